@@ -1,0 +1,253 @@
+/*
+ * Control-plane bootstrap for one NVSwitch box: a star of abstract AF_UNIX stream sockets.
+ *
+ * Replaces, for the single-box scope of this build, the reference's NCCL-based host collectives
+ * (cpp/src/wholememory/nccl_comms.cpp:210-232 host_allgather, :383-407 host_alltoall, :82-86
+ * barrier) and its AF_UNIX SCM_RIGHTS file-descriptor exchange
+ * (cpp/src/wholememory/memory_handle.cpp:746-943).  One mechanism carries both bytes and fds,
+ * needs no GPU, no NCCL and no temp directory, so the control plane is testable on a CPU box.
+ */
+#include "wm_internal.hpp"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <poll.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <time.h>
+#include <unistd.h>
+
+namespace wm {
+
+namespace {
+
+constexpr int kConnectTimeoutMs = 120000;
+
+socklen_t make_addr(const wholememory_unique_id_t& uid, sockaddr_un* addr)
+{
+  memset(addr, 0, sizeof(*addr));
+  addr->sun_family = AF_UNIX;
+  /* abstract namespace: sun_path[0] == 0; name = "wgb200-" + 24 hex chars of the id */
+  char* p = addr->sun_path + 1;
+  int n   = snprintf(p, sizeof(addr->sun_path) - 1, "wgb200-");
+  for (int i = 0; i < 12; ++i) n += snprintf(p + n, sizeof(addr->sun_path) - 1 - n, "%02x", (unsigned char)uid.internal[i]);
+  return (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+
+int64_t now_ms()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (int64_t)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
+}
+
+}  // namespace
+
+void bootstrap::send_all(int fd, const void* p, size_t n)
+{
+  const char* c = static_cast<const char*>(p);
+  while (n > 0) {
+    ssize_t w = ::send(fd, c, n, MSG_NOSIGNAL);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap send failed: %s", strerror(errno));
+    }
+    c += w;
+    n -= (size_t)w;
+  }
+}
+
+void bootstrap::recv_all(int fd, void* p, size_t n)
+{
+  char* c = static_cast<char*>(p);
+  while (n > 0) {
+    ssize_t r = ::recv(fd, c, n, 0);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap recv failed: %s", strerror(errno));
+    }
+    if (r == 0) WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap peer closed the connection");
+    c += r;
+    n -= (size_t)r;
+  }
+}
+
+/* one byte of payload says whether an fd rides along */
+void bootstrap::send_fd(int sock, int fd)
+{
+  char tag = fd >= 0 ? 1 : 0;
+  if (fd < 0) {
+    send_all(sock, &tag, 1);
+    return;
+  }
+  msghdr msg{};
+  iovec iov{&tag, 1};
+  alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+  memset(ctrl, 0, sizeof(ctrl));
+  msg.msg_iov        = &iov;
+  msg.msg_iovlen     = 1;
+  msg.msg_control    = ctrl;
+  msg.msg_controllen = sizeof(ctrl);
+  cmsghdr* c         = CMSG_FIRSTHDR(&msg);
+  c->cmsg_level      = SOL_SOCKET;
+  c->cmsg_type       = SCM_RIGHTS;
+  c->cmsg_len        = CMSG_LEN(sizeof(int));
+  memcpy(CMSG_DATA(c), &fd, sizeof(int));
+  for (;;) {
+    ssize_t w = ::sendmsg(sock, &msg, MSG_NOSIGNAL);
+    if (w < 0 && errno == EINTR) continue;
+    if (w != 1) WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap sendmsg(fd) failed: %s", strerror(errno));
+    break;
+  }
+}
+
+int bootstrap::recv_fd(int sock)
+{
+  char tag = 0;
+  msghdr msg{};
+  iovec iov{&tag, 1};
+  alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+  memset(ctrl, 0, sizeof(ctrl));
+  msg.msg_iov        = &iov;
+  msg.msg_iovlen     = 1;
+  msg.msg_control    = ctrl;
+  msg.msg_controllen = sizeof(ctrl);
+  for (;;) {
+    ssize_t r = ::recvmsg(sock, &msg, MSG_CMSG_CLOEXEC);
+    if (r < 0 && errno == EINTR) continue;
+    if (r != 1) WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap recvmsg(fd) failed: %s", strerror(errno));
+    break;
+  }
+  if (tag == 0) return -1;
+  cmsghdr* c = CMSG_FIRSTHDR(&msg);
+  if (c == nullptr || c->cmsg_level != SOL_SOCKET || c->cmsg_type != SCM_RIGHTS)
+    WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap expected a file descriptor, got none");
+  int fd = -1;
+  memcpy(&fd, CMSG_DATA(c), sizeof(int));
+  return fd;
+}
+
+bootstrap::bootstrap(const wholememory_unique_id_t& uid, int rank, int size) : rank_(rank), size_(size)
+{
+  WM_EXPECT(size >= 1 && rank >= 0 && rank < size, WHOLEMEMORY_INVALID_INPUT, "bad rank %d / size %d", rank, size);
+  if (size == 1) return;
+  sockaddr_un addr;
+  socklen_t alen = make_addr(uid, &addr);
+  if (rank == 0) {
+    peers_.assign(size, -1);
+    listen_fd_ = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    WM_EXPECT(listen_fd_ >= 0, WHOLEMEMORY_SYSTEM_ERROR, "socket(): %s", strerror(errno));
+    if (::bind(listen_fd_, (sockaddr*)&addr, alen) != 0)
+      WM_THROW(WHOLEMEMORY_SYSTEM_ERROR, "bootstrap bind failed (unique id reused?): %s", strerror(errno));
+    WM_EXPECT(::listen(listen_fd_, size) == 0, WHOLEMEMORY_SYSTEM_ERROR, "listen(): %s", strerror(errno));
+    int64_t deadline = now_ms() + kConnectTimeoutMs;
+    for (int got = 1; got < size;) {
+      pollfd pfd{listen_fd_, POLLIN, 0};
+      int remaining = (int)(deadline - now_ms());
+      if (remaining <= 0 || ::poll(&pfd, 1, remaining) <= 0)
+        WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap: only %d of %d ranks connected", got, size);
+      int s = ::accept4(listen_fd_, nullptr, nullptr, SOCK_CLOEXEC);
+      if (s < 0) continue;
+      int32_t peer_rank = -1;
+      recv_all(s, &peer_rank, sizeof(peer_rank));
+      WM_EXPECT(peer_rank > 0 && peer_rank < size && peers_[peer_rank] < 0,
+                WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap: unexpected rank %d", peer_rank);
+      peers_[peer_rank] = s;
+      ++got;
+    }
+    ::close(listen_fd_); /* nobody else may join; frees the abstract name */
+    listen_fd_ = -1;
+  } else {
+    peers_.assign(1, -1);
+    int64_t deadline = now_ms() + kConnectTimeoutMs;
+    for (;;) {
+      int s = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+      WM_EXPECT(s >= 0, WHOLEMEMORY_SYSTEM_ERROR, "socket(): %s", strerror(errno));
+      if (::connect(s, (sockaddr*)&addr, alen) == 0) {
+        peers_[0] = s;
+        break;
+      }
+      ::close(s);
+      if (now_ms() > deadline)
+        WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap: rank %d could not reach rank 0: %s", rank, strerror(errno));
+      usleep(2000);
+    }
+    int32_t me = rank;
+    send_all(peers_[0], &me, sizeof(me));
+  }
+  barrier();
+}
+
+bootstrap::~bootstrap()
+{
+  for (int s : peers_)
+    if (s >= 0) ::close(s);
+  if (listen_fd_ >= 0) ::close(listen_fd_);
+}
+
+void bootstrap::allgather(const void* send, void* recv, size_t bytes)
+{
+  if (size_ == 1) {
+    if (recv != send) memcpy(recv, send, bytes);
+    return;
+  }
+  char* out = static_cast<char*>(recv);
+  if (rank_ == 0) {
+    memmove(out, send, bytes);
+    for (int r = 1; r < size_; ++r) recv_all(peers_[r], out + (size_t)r * bytes, bytes);
+    for (int r = 1; r < size_; ++r) send_all(peers_[r], out, bytes * size_);
+  } else {
+    send_all(peers_[0], send, bytes);
+    recv_all(peers_[0], out, bytes * size_);
+  }
+}
+
+void bootstrap::barrier()
+{
+  char token = 0;
+  std::vector<char> all(size_);
+  allgather(&token, all.data(), 1);
+}
+
+void bootstrap::broadcast(void* buf, size_t bytes, int root)
+{
+  if (size_ == 1) return;
+  std::vector<char> all(bytes * size_);
+  allgather(buf, all.data(), bytes);
+  memcpy(buf, all.data() + (size_t)root * bytes, bytes);
+}
+
+void bootstrap::alltoall(const void* send, void* recv, size_t bytes)
+{
+  if (size_ == 1) {
+    if (recv != send) memcpy(recv, send, bytes);
+    return;
+  }
+  /* small payloads only (per-rank counts): gather the whole matrix, keep our column */
+  std::vector<char> all(bytes * size_ * size_);
+  allgather(send, all.data(), bytes * size_);
+  char* out = static_cast<char*>(recv);
+  for (int src = 0; src < size_; ++src)
+    memcpy(out + (size_t)src * bytes, all.data() + ((size_t)src * size_ + rank_) * bytes, bytes);
+}
+
+std::vector<int> bootstrap::allgather_fds(int my_fd)
+{
+  std::vector<int> fds(size_, -1);
+  if (size_ == 1) {
+    fds[0] = my_fd >= 0 ? ::dup(my_fd) : -1;
+    return fds;
+  }
+  if (rank_ == 0) {
+    fds[0] = my_fd >= 0 ? ::dup(my_fd) : -1;
+    for (int r = 1; r < size_; ++r) fds[r] = recv_fd(peers_[r]);
+    for (int r = 1; r < size_; ++r)
+      for (int src = 0; src < size_; ++src) send_fd(peers_[r], fds[src]);
+  } else {
+    send_fd(peers_[0], my_fd);
+    for (int src = 0; src < size_; ++src) fds[src] = recv_fd(peers_[0]);
+  }
+  return fds;
+}
+
+}  // namespace wm

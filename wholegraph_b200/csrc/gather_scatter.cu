@@ -1,0 +1,161 @@
+/*
+ * Host-side planning + launch for the row gather/scatter kernels (gather_scatter.cuh).
+ * Replaces the reference's gather_temp_func / scatter_temp_func launch logic
+ * (cpp/src/wholememory_ops/functions/gather_scatter_func.cuh:378-517, :600-661) and its
+ * dtype-pair registry (register.hpp): same accepted dtype pairs plus bf16.
+ */
+#include "gather_scatter.cuh"
+#include "ops_internal.hpp"
+
+#include <algorithm>
+
+namespace wm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll  = 4;
+
+inline int pow2_divisor(uint64_t v, int cap)
+{
+  int a = cap;
+  while (a > 1 && (v % (uint64_t)a) != 0) a >>= 1;
+  return a;
+}
+
+template <typename IdxT, int VEC, bool GATHER>
+void launch_vec(const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
+{
+  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, kThreads, 0, s>>>(t, g, static_cast<const IdxT*>(idx), n, dense);
+}
+
+template <typename IdxT, bool GATHER>
+void launch_vec_w(int vec, const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
+{
+  switch (vec) {
+    case 16: launch_vec<IdxT, 16, GATHER>(t, g, idx, n, dense, grid, s); break;
+    case 8: launch_vec<IdxT, 8, GATHER>(t, g, idx, n, dense, grid, s); break;
+    case 4: launch_vec<IdxT, 4, GATHER>(t, g, idx, n, dense, grid, s); break;
+    case 2: launch_vec<IdxT, 2, GATHER>(t, g, idx, n, dense, grid, s); break;
+    default: launch_vec<IdxT, 1, GATHER>(t, g, idx, n, dense, grid, s); break;
+  }
+}
+
+int vec_blocks_per_sm()
+{
+  static int occ = [] {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, kUnroll>, kThreads, 0) != cudaSuccess || o <= 0) {
+      (void)cudaGetLastError();
+      o = 4;
+    }
+    return o;
+  }();
+  return occ;
+}
+
+/* rows per warp batch + grid size.  Enough batches to balance the persistent grid, small enough
+ * batches that one warp does not serialise a long copy. */
+void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_rows, int* grid)
+{
+  int total_sms = sm_count();
+  if (sms <= 0 || sms > total_sms) sms = total_sms;
+  int64_t max_grid    = (int64_t)sms * blocks_per_sm;
+  int64_t total_warps = max_grid * (kThreads / 32);
+  int R               = 32;
+  while (R > 1 && (int64_t)R * row_bytes > 16384) R >>= 1;
+  while (R > 1 && n / R < total_warps * 4) R >>= 1;
+  int64_t nbatch = (n + R - 1) / R;
+  int64_t need   = (nbatch + (kThreads / 32) - 1) / (kThreads / 32);
+  *batch_rows    = R;
+  *grid          = (int)std::max<int64_t>(1, std::min(max_grid, need));
+}
+
+}  // namespace
+
+table_ref make_flat_table_ref(void* base)
+{
+  table_ref t{};
+  t.mode    = table_ref::FLAT;
+  t.nranks  = 1;
+  t.base[0] = static_cast<char*>(base);
+  return t;
+}
+
+void row_move(bool gather,
+              const table_ref& tref,
+              const wholememory_matrix_description_t& td,
+              const void* indices,
+              const wholememory_array_description_t& idx_desc,
+              void* dense,
+              const wholememory_matrix_description_t& dd,
+              cudaStream_t stream,
+              int sms)
+{
+  require_cuda(gather ? "wholememory_gather" : "wholememory_scatter");
+  const bool t_float = wholememory_dtype_is_floating_number(td.dtype);
+  const bool d_float = wholememory_dtype_is_floating_number(dd.dtype);
+  WM_EXPECT(t_float || wholememory_dtype_is_integer_number(td.dtype), WHOLEMEMORY_LOGIC_ERROR, "table dtype %d unsupported", (int)td.dtype);
+  WM_EXPECT(d_float || wholememory_dtype_is_integer_number(dd.dtype), WHOLEMEMORY_LOGIC_ERROR, "dense dtype %d unsupported", (int)dd.dtype);
+  /* reference gather_func.cu:78-81 */
+  WM_EXPECT(t_float == d_float, WHOLEMEMORY_LOGIC_ERROR,
+            "table and %s must both be floating point or both be integer", gather ? "output" : "input");
+  WM_EXPECT(idx_desc.dtype == WHOLEMEMORY_DT_INT || idx_desc.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR,
+            "indices must be int32 or int64");
+  const int64_t n = idx_desc.size;
+  WM_EXPECT(dd.sizes[0] == n, WHOLEMEMORY_LOGIC_ERROR, "%s rows=%ld but indice_count=%ld",
+            gather ? "output" : "input", (long)dd.sizes[0], (long)n);
+  WM_EXPECT(dd.sizes[1] == td.sizes[1], WHOLEMEMORY_LOGIC_ERROR, "row width mismatch: table %ld vs %ld",
+            (long)td.sizes[1], (long)dd.sizes[1]);
+  if (n == 0 || td.sizes[1] == 0) return;
+  WM_EXPECT(indices != nullptr && dense != nullptr, WHOLEMEMORY_INVALID_INPUT, "null indices / data pointer");
+
+  const int64_t et = (int64_t)wholememory_dtype_get_element_size(td.dtype);
+  const int64_t ed = (int64_t)wholememory_dtype_get_element_size(dd.dtype);
+  const bool idx64 = idx_desc.dtype == WHOLEMEMORY_DT_INT64;
+  const char* idx_ptr = static_cast<const char*>(indices) + idx_desc.storage_offset * (idx64 ? 8 : 4);
+  char* dense_ptr     = static_cast<char*>(dense) + dd.storage_offset * ed;
+
+  row_geom g{};
+  g.table_offset_bytes = td.storage_offset * et;
+  g.table_stride_bytes = td.stride * et;
+  g.dense_stride_bytes = dd.stride * ed;
+
+  /* alignment shared by both sides, in bytes of each side's element */
+  uint64_t t_bits = (uint64_t)g.table_offset_bytes | (uint64_t)g.table_stride_bytes;
+  if (tref.mode == table_ref::FLAT) t_bits |= reinterpret_cast<uint64_t>(tref.base[0]);
+  uint64_t d_bits = reinterpret_cast<uint64_t>(dense_ptr) | (uint64_t)g.dense_stride_bytes;
+
+  if (td.dtype == dd.dtype) {
+    const int64_t row_bytes = td.sizes[1] * et;
+    int vec                 = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, 16);
+    g.row_elems             = (int)(row_bytes / vec);
+    int grid                = 1;
+    plan(n, row_bytes, sms, vec_blocks_per_sm(), &g.batch_rows, &grid);
+    if (gather) {
+      if (idx64) launch_vec_w<int64_t, true>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);
+      else launch_vec_w<int32_t, true>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);
+    } else {
+      if (idx64) launch_vec_w<int64_t, false>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);
+      else launch_vec_w<int32_t, false>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);
+    }
+  } else {
+    /* elements per lane: both vectors <= 16 bytes and aligned (reference :215-251, :395-397) */
+    int cap   = (int)(16 / std::max(et, ed));
+    int a_t   = pow2_divisor(t_bits / (uint64_t)et | (uint64_t)td.sizes[1], cap);
+    int a_d   = pow2_divisor(d_bits / (uint64_t)ed | (uint64_t)td.sizes[1], cap);
+    /* t_bits/d_bits are multiples of the element size by construction of the descriptors */
+    int align = std::min(a_t, a_d);
+    g.row_elems = (int)td.sizes[1];
+    int grid    = 1;
+    plan(n, td.sizes[1] * std::max(et, ed), sms, cvt_blocks_per_sm(), &g.batch_rows, &grid);
+    cvt_launch_fn fn = t_float ? find_float_cvt(td.dtype, dd.dtype) : find_int_cvt(td.dtype, dd.dtype);
+    WM_EXPECT(fn != nullptr, WHOLEMEMORY_LOGIC_ERROR, "no conversion kernel for dtype %d -> %d", (int)td.dtype, (int)dd.dtype);
+    fn(gather, tref, g, idx_ptr, idx64, n, dense_ptr, align, grid, stream);
+  }
+  WM_CUDA(cudaGetLastError());
+  static const bool debug_sync = getenv("WM_DEBUG_SYNC") != nullptr; /* reference cuda_macros.cpp:27-66 */
+  if (debug_sync) WM_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace wm

@@ -1,0 +1,30 @@
+/* Plain (host + device) structs handed to the row-move kernels by value. */
+#pragma once
+#include <stdint.h>
+
+namespace wm {
+
+constexpr int kMaxInlineRanks = 16;
+
+/* How a kernel finds table row bytes.  Passed BY VALUE as a kernel parameter. */
+struct table_ref {
+  enum : int { FLAT = 0, CHUNK_REGULAR = 1, CHUNK_IRREGULAR = 2, DEVTAB_REGULAR = 3, DEVTAB_IRREGULAR = 4 };
+  int mode;
+  int nranks;
+  uint64_t chunk_bytes;                        /* *_REGULAR: bytes owned by each rank */
+  char* base[kMaxInlineRanks];                 /* FLAT: base[0]; CHUNK_*: start of rank r's partition */
+  uint64_t first_byte[kMaxInlineRanks + 1];    /* CHUNK_IRREGULAR: partition start offsets */
+  char* const* dev_bases;                      /* DEVTAB_*: public gref tables in device memory */
+  const uint64_t* dev_first_byte;
+};
+
+/* strided matrix geometry in BYTES (host computes these once) */
+struct row_geom {
+  int64_t table_offset_bytes; /* storage_offset * esize */
+  int64_t table_stride_bytes;
+  int64_t dense_stride_bytes;
+  int row_elems;   /* columns */
+  int batch_rows;  /* rows resolved per warp batch: power of two <= 32 */
+};
+
+}  // namespace wm
