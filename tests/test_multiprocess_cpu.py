@@ -1,0 +1,81 @@
+"""world_size-2 tests of the multi-rank HOST logic on a CPU box: torch.distributed (gloo) carries the
+unique id exactly like the reference's comm.py, the library's own AF_UNIX bootstrap does the rest
+(rank discovery, collectives, fd passing, split).  No GPU needed."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import wholegraph_b200.binding as wmb
+    import wholegraph_b200.torch as wgth
+    from wholegraph_b200 import _lib
+    try:
+        wgth.init_torch_env(rank, world_size, rank, world_size, wm_log_level="warn", backend="gloo")
+        comm = wgth.get_global_communicator()
+        assert comm.get_rank() == rank and comm.get_size() == world_size
+        assert wgth.get_local_node_communicator() is comm
+        # every rank must agree that nothing device-mapped can be allocated on a GPU-less box
+        assert comm.support_type_location("distributed", "cuda")
+        assert comm.support_type_location("continuous", "cuda") == torch.cuda.is_available()
+        # split: ranks with the same color form a new communicator ordered by key
+        sub = wgth.split_communicator(comm, color=rank % 2, key=0)
+        assert sub.get_size() == (world_size + 1 - rank % 2) // 2 and sub.get_rank() == rank // 2
+        sub.destroy()
+        # a second communicator in the reverse order of creation still matches ranks up
+        comm2 = wgth.create_group_communicator()
+        assert comm2.get_rank() == rank
+        wgth.destroy_communicator(comm2)
+        # collective argument check: different sizes on different ranks must be rejected, not deadlock
+        if not torch.cuda.is_available():
+            try:
+                wmb.malloc(1024 * (rank + 1), comm.wmb_comm, wmb.MtDistributed, wmb.MlDevice, 64)
+                ok = False
+            except RuntimeError:
+                ok = True
+            assert ok
+        results[rank] = "ok"
+    except Exception as e:  # pragma: no cover
+        import traceback
+        results[rank] = "FAIL: " + traceback.format_exc()
+    finally:
+        try:
+            wgth.finalize()
+        except Exception:
+            pass
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_control_plane_world_size_n_over_gloo(world_size):
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world_size, port, results)) for r in range(world_size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("rank hung")
+    assert dict(results) == {r: "ok" for r in range(world_size)}, dict(results)

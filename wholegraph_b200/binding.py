@@ -1,0 +1,781 @@
+"""Python binding over the C ABI -- the ctypes counterpart of the reference's cython module
+``pylibwholegraph.binding.wholememory_binding`` (``wholememory_binding.pyx``): same class and
+function names, same argument meaning, same exceptions per error code (pyx:255-277), so the
+torch-level layer (``wholegraph_b200.torch``) reads like ``pylibwholegraph.torch``.
+
+Views of WholeMemory are handed out as ``torch`` tensors built on the raw device/host pointer
+(the reference exports DLPack capsules, pyx:1105-1295; zero-copy either way).
+"""
+import ctypes
+import enum
+from ctypes import POINTER, byref, c_int, c_int64, c_size_t, c_void_p
+
+from . import _lib
+from ._lib import lib
+
+
+class WholeMemoryErrorCode(enum.IntEnum):
+    Success = 0
+    UnknowError = 1
+    NotImplemented = 2
+    LogicError = 3
+    CUDAError = 4
+    CommunicationError = 5
+    InvalidInput = 6
+    InvalidValue = 7
+    OutOfMemory = 8
+    NotSupported = 9
+    SystemError = 10
+
+
+class WholeMemoryMemoryType(enum.IntEnum):
+    MtNone = 0
+    MtContinuous = 1
+    MtChunked = 2
+    MtDistributed = 3
+    MtHierarchy = 4
+
+
+class WholeMemoryMemoryLocation(enum.IntEnum):
+    MlNone = 0
+    MlDevice = 1
+    MlHost = 2
+
+
+class WholeMemoryDistributedBackend(enum.IntEnum):
+    DbNone = 0
+    DbNCCL = 1
+    DbNVSHMEM = 2
+
+
+class WholeMemoryLogLevel(enum.IntEnum):
+    LevFatal = 0
+    LevError = 1
+    LevWarn = 2
+    LevInfo = 3
+    LevDebug = 4
+    LevTrace = 5
+
+
+class WholeMemoryMemoryAllocType(enum.IntEnum):
+    MatNone = 0
+    MatDevice = 1
+    MatHost = 2
+    MatPinned = 3
+
+
+class WholeMemoryDataType(enum.IntEnum):
+    DtUnknown = 0
+    DtFloat = 1
+    DtHalf = 2
+    DtDouble = 3
+    DtBF16 = 4
+    DtInt = 5
+    DtInt64 = 6
+    DtInt16 = 7
+    DtInt8 = 8
+    DtCount = 9
+
+
+class WholeMemoryAccessType(enum.IntEnum):
+    AtNone = 0
+    AtReadOnly = 1
+    AtReadWrite = 2
+
+
+class WholeMemoryOptimizerType(enum.IntEnum):
+    OptNone = 0
+    OptSgd = 1
+    OptLazyAdam = 2
+    OptRmsProp = 3
+    OptAdaGrad = 4
+
+
+class WholeMemoryViewType(enum.IntEnum):
+    VtNone = 0
+    VtLocal = 1
+    VtGlobal = 2
+    VtRemote = 3
+
+
+# export enum members at module level like a cpdef enum does
+for _e in (WholeMemoryErrorCode, WholeMemoryMemoryType, WholeMemoryMemoryLocation, WholeMemoryDistributedBackend,
+           WholeMemoryLogLevel, WholeMemoryMemoryAllocType, WholeMemoryDataType, WholeMemoryAccessType,
+           WholeMemoryOptimizerType, WholeMemoryViewType):
+    for _m in _e:
+        if _m.name not in ("NotImplemented", "SystemError"):
+            globals()[_m.name] = _m
+
+
+def check_wholememory_error_code(err):
+    """Same mapping as the reference binding (pyx:255-277)."""
+    err = int(err)
+    if err == 0:
+        return
+    if err == WholeMemoryErrorCode.UnknowError:
+        raise Exception("Unknown error")
+    if err == WholeMemoryErrorCode.NotImplemented:
+        raise NotImplementedError("Not implemented")
+    if err == WholeMemoryErrorCode.LogicError:
+        raise RuntimeError("Logic error")
+    if err == WholeMemoryErrorCode.CUDAError:
+        raise RuntimeError("CUDA error")
+    if err == WholeMemoryErrorCode.CommunicationError:
+        raise RuntimeError("Communication error")
+    if err == WholeMemoryErrorCode.InvalidInput:
+        raise ValueError("Invalid input")
+    if err == WholeMemoryErrorCode.InvalidValue:
+        raise ValueError("Invalid value")
+    if err == WholeMemoryErrorCode.OutOfMemory:
+        raise MemoryError("Out of memory")
+    raise NotImplementedError("Error code %d not recognized" % err)
+
+
+_chk = check_wholememory_error_code
+
+
+def get_type_string(data_type):
+    return {
+        WholeMemoryDataType.DtFloat: "<f4", WholeMemoryDataType.DtHalf: "<f2", WholeMemoryDataType.DtDouble: "<f8",
+        WholeMemoryDataType.DtBF16: "<f2", WholeMemoryDataType.DtInt: "<i4", WholeMemoryDataType.DtInt64: "<i8",
+        WholeMemoryDataType.DtInt16: "<i2", WholeMemoryDataType.DtInt8: "|i1",
+    }[WholeMemoryDataType(data_type)]
+
+
+# --------------------------------------------------------------------------- init / ids
+def init(flags=0, log_level=WholeMemoryLogLevel.LevInfo):
+    _chk(lib.wholememory_init(flags, int(log_level)))
+
+
+def finalize():
+    _chk(lib.wholememory_finalize())
+
+
+def fork_get_gpu_count():
+    return lib.fork_get_device_count()
+
+
+def py_get_wholememory_tensor_count():
+    return lib.get_wholememory_tensor_count()
+
+
+class PyWholeMemoryUniqueID:
+    """128-byte communicator id; exposes a writable buffer so it can be broadcast."""
+
+    def __init__(self):
+        self.c = _lib.UniqueId()
+
+    def __len__(self):
+        return _lib.WHOLEMEMORY_UNIQUE_ID_BYTES
+
+    def as_bytes(self):
+        return ctypes.string_at(ctypes.addressof(self.c), len(self))
+
+    def set_bytes(self, b):
+        assert len(b) == len(self)
+        ctypes.memmove(ctypes.addressof(self.c), bytes(b), len(self))
+
+    def as_tensor(self):
+        """int8 torch view sharing memory with the id (reference: uid.__dlpack__())."""
+        import torch
+        buf = (ctypes.c_int8 * len(self)).from_address(ctypes.addressof(self.c))
+        t = torch.frombuffer(buf, dtype=torch.int8)
+        t._wm_keepalive = self
+        return t
+
+
+def create_unique_id():
+    uid = PyWholeMemoryUniqueID()
+    _chk(lib.wholememory_create_unique_id(byref(uid.c)))
+    return uid
+
+
+# --------------------------------------------------------------------------- communicator
+class PyWholeMemoryComm:
+    def __init__(self, c_handle=None):
+        self.comm_id = c_void_p(c_handle)
+
+    def get_c_handle(self):
+        return self.comm_id.value
+
+    def support_type_location(self, memory_type, memory_location):
+        return lib.wholememory_communicator_support_type_location(self.comm_id, int(memory_type),
+                                                                  int(memory_location)) == 0
+
+    def get_rank(self):
+        r = c_int(-1)
+        _chk(lib.wholememory_communicator_get_rank(byref(r), self.comm_id))
+        return r.value
+
+    def get_size(self):
+        s = c_int(-1)
+        _chk(lib.wholememory_communicator_get_size(byref(s), self.comm_id))
+        return s.value
+
+    def get_clique_info(self):
+        ci = _lib.CliqueInfo()
+        _chk(lib.wholememory_communicator_get_clique_info(byref(ci), self.comm_id))
+        cf = ci.clique_first_rank if ci.is_in_clique > 0 else -1
+        cr = ci.clique_rank if ci.is_in_clique > 0 else -1
+        cn = ci.clique_rank_num if ci.is_in_clique > 0 else -1
+        return ci.is_in_clique > 0, cf, cr, cn, ci.clique_id, ci.clique_num
+
+    def barrier(self):
+        _chk(lib.wholememory_communicator_barrier(self.comm_id))
+
+    def get_distributed_backend(self):
+        return WholeMemoryDistributedBackend(lib.wholememory_communicator_get_distributed_backend(self.comm_id))
+
+    def set_distributed_backend(self, distributed_backend):
+        _chk(lib.wholememory_communicator_set_distributed_backend(self.comm_id, int(distributed_backend)))
+
+
+def create_communicator(py_uid, world_rank, world_size):
+    comm = c_void_p()
+    _chk(lib.wholememory_create_communicator(byref(comm), py_uid.c, world_rank, world_size))
+    return PyWholeMemoryComm(comm.value)
+
+
+def destroy_communicator(py_comm):
+    _chk(lib.wholememory_destroy_communicator(py_comm.comm_id))
+    py_comm.comm_id = c_void_p(None)
+
+
+def split_communicator(comm, color, key):
+    new_comm = c_void_p()
+    _chk(lib.wholememory_split_communicator(byref(new_comm), comm.comm_id, color, key))
+    return PyWholeMemoryComm(new_comm.value)
+
+
+def communicator_set_distributed_backend(py_comm, distributed_backend):
+    py_comm.set_distributed_backend(distributed_backend)
+
+
+def equal_partition_plan(entry_count, world_size):
+    per = c_size_t(0)
+    _chk(lib.wholememory_equal_entry_partition_plan(byref(per), entry_count, world_size))
+    return per.value
+
+
+# --------------------------------------------------------------------------- raw views as torch tensors
+_TORCH_DTYPES = None
+
+
+def _torch_dtype(dt):
+    global _TORCH_DTYPES
+    import torch
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {
+            WholeMemoryDataType.DtFloat: torch.float32, WholeMemoryDataType.DtHalf: torch.float16,
+            WholeMemoryDataType.DtDouble: torch.float64, WholeMemoryDataType.DtBF16: torch.bfloat16,
+            WholeMemoryDataType.DtInt: torch.int32, WholeMemoryDataType.DtInt64: torch.int64,
+            WholeMemoryDataType.DtInt16: torch.int16, WholeMemoryDataType.DtInt8: torch.int8,
+        }
+    return _TORCH_DTYPES[WholeMemoryDataType(dt)]
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ provider over a raw device pointer."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+def _view_as_torch(ptr, nbytes, dtype, location, device_id, owner):
+    """uint8 view of [ptr, ptr+nbytes) reinterpreted as dtype.  location: MlDevice -> cuda tensor."""
+    import torch
+    tdt = _torch_dtype(dtype)
+    if nbytes == 0 or not ptr:
+        dev = ("cuda:%d" % device_id) if location == WholeMemoryMemoryLocation.MlDevice else "cpu"
+        return torch.empty(0, dtype=tdt, device=dev)
+    if location == WholeMemoryMemoryLocation.MlDevice:
+        t = torch.as_tensor(_CudaArray(ptr, nbytes, owner), device="cuda:%d" % device_id)
+    else:
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        t = torch.frombuffer(buf, dtype=torch.uint8)
+        t._wm_keepalive = owner
+    return t.view(tdt)
+
+
+# --------------------------------------------------------------------------- handles / tensors
+class PyWholeMemoryHandle:
+    def __init__(self, c_handle=None):
+        self.wholememory_handle = c_void_p(c_handle)
+
+    def get_c_handle(self):
+        return self.wholememory_handle.value
+
+    def get_communicator(self):
+        comm = c_void_p()
+        _chk(lib.wholememory_get_communicator(byref(comm), self.wholememory_handle))
+        return PyWholeMemoryComm(comm.value)
+
+    def get_memory_type(self):
+        return WholeMemoryMemoryType(lib.wholememory_get_memory_type(self.wholememory_handle))
+
+    def get_memory_location(self):
+        return WholeMemoryMemoryLocation(lib.wholememory_get_memory_location(self.wholememory_handle))
+
+    def get_total_size(self):
+        return lib.wholememory_get_total_size(self.wholememory_handle)
+
+    def get_local_memory(self):
+        p, s, o = c_void_p(), c_size_t(), c_size_t()
+        _chk(lib.wholememory_get_local_memory(byref(p), byref(s), byref(o), self.wholememory_handle))
+        return p.value, s.value, o.value
+
+    def get_rank_memory(self, rank):
+        p, s, o = c_void_p(), c_size_t(), c_size_t()
+        _chk(lib.wholememory_get_rank_memory(byref(p), byref(s), byref(o), rank, self.wholememory_handle))
+        return p.value, s.value, o.value
+
+    def get_global_pointer(self):
+        p = c_void_p()
+        _chk(lib.wholememory_get_global_pointer(byref(p), self.wholememory_handle))
+        return p.value
+
+    def get_global_reference(self):
+        g = _lib.GlobalReference()
+        _chk(lib.wholememory_get_global_reference(byref(g), self.wholememory_handle))
+        return g
+
+    def get_rank_partition_offsets(self):
+        n = self.get_communicator().get_size()
+        arr = (c_size_t * (n + 1))()
+        _chk(lib.wholememory_get_rank_partition_offsets(arr, self.wholememory_handle))
+        return list(arr)
+
+    # torch views (reference: get_local_flatten_tensor / get_global_flatten_tensor / get_all_chunked_flatten_tensor)
+    def get_local_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+        p, s, o = self.get_local_memory()
+        es = lib.wholememory_dtype_get_element_size(int(dtype))
+        return _view_as_torch(p, s, dtype, self._view_loc(view_from_location), view_from_device_id, self), o // es
+
+    def get_global_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+        p = self.get_global_pointer()
+        return _view_as_torch(p, self.get_total_size(), dtype, self._view_loc(view_from_location),
+                              view_from_device_id, self), 0
+
+    def get_all_chunked_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+        n = self.get_communicator().get_size()
+        es = lib.wholememory_dtype_get_element_size(int(dtype))
+        tensors, offsets = [], []
+        for r in range(n):
+            p, s, o = self.get_rank_memory(r)
+            tensors.append(_view_as_torch(p, s, dtype, self._view_loc(view_from_location), view_from_device_id, self))
+            offsets.append(o // es)
+        return tensors, offsets
+
+    def _view_loc(self, view_from_location):
+        loc = self.get_memory_location()
+        view = WholeMemoryMemoryLocation(view_from_location)
+        if loc == WholeMemoryMemoryLocation.MlDevice and view == WholeMemoryMemoryLocation.MlHost:
+            raise ValueError("Device WholeMemory cannot get view from host.")
+        return view
+
+    def from_filelist(self, memory_offset, memory_entry_size, file_entry_size, round_robin_size, file_list):
+        arr = (ctypes.c_char_p * len(file_list))(*[f.encode() for f in file_list])
+        _chk(lib.wholememory_load_from_file(self.wholememory_handle, memory_offset, memory_entry_size, file_entry_size,
+                                            arr, len(file_list), round_robin_size))
+
+    def to_file(self, memory_offset, memory_entry_size, file_entry_size, file_name):
+        _chk(lib.wholememory_store_to_file(self.wholememory_handle, memory_offset, memory_entry_size, file_entry_size,
+                                           file_name.encode()))
+
+
+class PyWholeMemoryTensorDescription:
+    def __init__(self):
+        self.tensor_description = _lib.TensorDescription()
+        lib.wholememory_initialize_tensor_desc(byref(self.tensor_description))
+
+    def set_dtype(self, dtype):
+        self.tensor_description.dtype = int(dtype)
+
+    def set_shape(self, shape):
+        assert 0 < len(shape) <= _lib.WHOLEMEMORY_MAX_TENSOR_DIM
+        self.tensor_description.dim = len(shape)
+        for i, s in enumerate(shape):
+            self.tensor_description.sizes[i] = int(s)
+
+    def set_stride(self, strides):
+        assert len(strides) == self.tensor_description.dim
+        for i, s in enumerate(strides):
+            self.tensor_description.strides[i] = int(s)
+
+    def set_storage_offset(self, storage_offset):
+        self.tensor_description.storage_offset = int(storage_offset)
+
+    @property
+    def dtype(self):
+        return WholeMemoryDataType(self.tensor_description.dtype)
+
+    def dim(self):
+        return self.tensor_description.dim
+
+    @property
+    def shape(self):
+        return tuple(self.tensor_description.sizes[i] for i in range(self.dim()))
+
+    def stride(self):
+        return tuple(self.tensor_description.strides[i] for i in range(self.dim()))
+
+    def storage_offset(self):
+        return self.tensor_description.storage_offset
+
+
+class WrappedLocalTensor:
+    """Non-owning wholememory_tensor_t over caller memory (indices, outputs, gradients)."""
+
+    def __init__(self):
+        self.wm_tensor = c_void_p(None)
+
+    def __del__(self):
+        if getattr(self, "wm_tensor", None) is not None and self.wm_tensor.value:
+            lib.wholememory_destroy_tensor(self.wm_tensor)
+            self.wm_tensor = c_void_p(None)
+
+    def wrap_tensor(self, py_desc, data_ptr):
+        _chk(lib.wholememory_make_tensor_from_pointer(byref(self.wm_tensor), c_void_p(data_ptr),
+                                                      byref(py_desc.tensor_description)))
+        return self
+
+    def get_c_handle(self):
+        return self.wm_tensor.value or 0
+
+
+class PyWholeMemoryTensor:
+    def __init__(self, c_tensor=None):
+        self.wholememory_tensor = c_void_p(c_tensor)
+
+    def get_c_handle(self):
+        return self.wholememory_tensor.value
+
+    def _desc(self):
+        return lib.wholememory_tensor_get_tensor_description(self.wholememory_tensor).contents
+
+    def get_wholememory_handle(self):
+        return PyWholeMemoryHandle(lib.wholememory_tensor_get_memory_handle(self.wholememory_tensor))
+
+    @property
+    def dtype(self):
+        return WholeMemoryDataType(self._desc().dtype)
+
+    def dim(self):
+        return self._desc().dim
+
+    @property
+    def shape(self):
+        d = self._desc()
+        return tuple(d.sizes[i] for i in range(d.dim))
+
+    def stride(self):
+        d = self._desc()
+        return tuple(d.strides[i] for i in range(d.dim))
+
+    def storage_offset(self):
+        return self._desc().storage_offset
+
+    def get_local_entry_count(self):
+        v = c_size_t()
+        _chk(lib.wholememory_tensor_get_local_entry_count(byref(v), self.wholememory_tensor))
+        return v.value
+
+    def get_local_entry_start(self):
+        v = c_size_t()
+        _chk(lib.wholememory_tensor_get_local_entry_start(byref(v), self.wholememory_tensor))
+        return v.value
+
+    def get_entry_offsets(self):
+        n = self.get_wholememory_handle().get_communicator().get_size()
+        arr = (c_size_t * (n + 1))()
+        _chk(lib.wholememory_tensor_get_entry_offsets(arr, self.wholememory_tensor))
+        return list(arr)
+
+    def get_sub_tensor(self, starts, ends):
+        d = self.dim()
+        if len(starts) != d or len(ends) != d:
+            raise ValueError("starts/ends must have one entry per dim")
+        s = (c_int64 * d)(*starts)
+        e = (c_int64 * d)(*ends)
+        sub = c_void_p()
+        _chk(lib.wholememory_tensor_get_subtensor(self.wholememory_tensor, s, e, byref(sub)))
+        return PyWholeMemoryTensor(sub.value)
+
+    def get_tensor_in_window(self, flatten_tensor, storage_window_offset):
+        """Reshape a flat view (element offset `storage_window_offset` from the handle start) to this tensor's
+        window, same arithmetic as the reference (pyx:1584-1610)."""
+        d = self._desc()
+        if d.dim == 1:
+            start_indice = max(0, d.storage_offset - storage_window_offset)
+            end_indice = min(flatten_tensor.shape[0], d.storage_offset + d.sizes[0] - storage_window_offset)
+            return flatten_tensor[start_indice:end_indice], max(0, storage_window_offset - d.storage_offset)
+        embedding_stride = d.strides[0]
+        storage_offset0 = d.storage_offset // embedding_stride
+        storage_offset1 = d.storage_offset % embedding_stride
+        mat = flatten_tensor.reshape(-1, embedding_stride)
+        assert storage_window_offset % embedding_stride == 0
+        vector_start_offset = storage_window_offset // embedding_stride
+        start_indice0 = max(0, storage_offset0 - vector_start_offset)
+        end_indice0 = min(mat.shape[0], storage_offset0 + d.sizes[0] - vector_start_offset)
+        return (mat[start_indice0:end_indice0, storage_offset1:storage_offset1 + d.sizes[1]],
+                max(0, vector_start_offset - storage_offset0))
+
+    def get_local_tensor(self, view_from_location, view_from_device_id):
+        flat, off = self.get_wholememory_handle().get_local_flatten_tensor(self.dtype, view_from_location,
+                                                                           view_from_device_id)
+        return self.get_tensor_in_window(flat, off)
+
+    def get_global_tensor(self, view_from_location, view_from_device_id):
+        flat, _ = self.get_wholememory_handle().get_global_flatten_tensor(self.dtype, view_from_location,
+                                                                          view_from_device_id)
+        return self.get_tensor_in_window(flat, 0)[0]
+
+    def get_all_chunked_tensor(self, view_from_location, view_from_device_id):
+        ts, offs = self.get_wholememory_handle().get_all_chunked_flatten_tensor(self.dtype, view_from_location,
+                                                                                view_from_device_id)
+        out_t, out_o = [], []
+        for t, o in zip(ts, offs):
+            tw, ow = self.get_tensor_in_window(t, o)
+            out_t.append(tw)
+            out_o.append(ow)
+        return out_t, out_o
+
+    def from_filelist(self, filelist, round_robin_size=0):
+        d = self._desc()
+        es = lib.wholememory_dtype_get_element_size(d.dtype)
+        stride = d.strides[0] if d.dim == 2 else 1
+        cols = d.sizes[1] if d.dim == 2 else 1
+        self.get_wholememory_handle().from_filelist(d.storage_offset * es, stride * es, cols * es, round_robin_size,
+                                                    filelist)
+
+    def to_file(self, filename):
+        d = self._desc()
+        es = lib.wholememory_dtype_get_element_size(d.dtype)
+        stride = d.strides[0] if d.dim == 2 else 1
+        cols = d.sizes[1] if d.dim == 2 else 1
+        self.get_wholememory_handle().to_file(d.storage_offset * es, stride * es, cols * es, filename)
+
+
+def malloc(total_size, py_comm, memory_type, memory_location, data_granularity, rank_entry_partition=None):
+    h = c_void_p()
+    part = None
+    if rank_entry_partition is not None:
+        part = (c_size_t * len(rank_entry_partition))(*rank_entry_partition)
+    _chk(lib.wholememory_malloc(byref(h), total_size, py_comm.comm_id, int(memory_type), int(memory_location),
+                                data_granularity, part))
+    return PyWholeMemoryHandle(h.value)
+
+
+def free(handle):
+    _chk(lib.wholememory_free(handle.wholememory_handle))
+
+
+def create_wholememory_tensor(tensor_description, comm, memory_type, memory_location, tensor_entry_partition=None):
+    if tensor_description.dim() not in (1, 2):
+        raise NotImplementedError("WholeMemory currently only support 1D or 2D tensor")
+    if tensor_description.stride()[tensor_description.dim() - 1] != 1:
+        raise ValueError("last stride should be 1")
+    if tensor_description.storage_offset() != 0:
+        raise ValueError("storage_offset be 0 when created")
+    t = c_void_p()
+    part = None
+    if tensor_entry_partition is not None:
+        part = (c_size_t * len(tensor_entry_partition))(*tensor_entry_partition)
+    _chk(lib.wholememory_create_tensor(byref(t), byref(tensor_description.tensor_description), comm.comm_id,
+                                       int(memory_type), int(memory_location), part))
+    return PyWholeMemoryTensor(t.value)
+
+
+def create_wholememory_array(dtype, size, comm, mem_type, mem_location, tensor_entry_partition=None):
+    d = PyWholeMemoryTensorDescription()
+    d.set_dtype(dtype)
+    d.set_shape((size,))
+    d.set_stride((1,))
+    return create_wholememory_tensor(d, comm, mem_type, mem_location, tensor_entry_partition)
+
+
+def create_wholememory_matrix(dtype, row, column, stride, comm, mem_type, mem_location, tensor_entry_partition=None):
+    d = PyWholeMemoryTensorDescription()
+    d.set_dtype(dtype)
+    d.set_shape((row, column))
+    d.set_stride((column if stride == -1 else stride, 1))
+    return create_wholememory_tensor(d, comm, mem_type, mem_location, tensor_entry_partition)
+
+
+def make_tensor_as_wholememory(tensor_description, data_ptr):
+    t = c_void_p()
+    _chk(lib.wholememory_make_tensor_from_pointer(byref(t), c_void_p(data_ptr),
+                                                  byref(tensor_description.tensor_description)))
+    return PyWholeMemoryTensor(t.value)
+
+
+def make_handle_as_wholememory(tensor_description, handle):
+    t = c_void_p()
+    _chk(lib.wholememory_make_tensor_from_handle(byref(t), handle.wholememory_handle,
+                                                 byref(tensor_description.tensor_description)))
+    return PyWholeMemoryTensor(t.value)
+
+
+def destroy_wholememory_tensor(wholememory_tensor):
+    _chk(lib.wholememory_destroy_tensor(wholememory_tensor.wholememory_tensor))
+    wholememory_tensor.wholememory_tensor = c_void_p(None)
+
+
+# --------------------------------------------------------------------------- ops
+def _env_ptr(p_env_fns_int):
+    return ctypes.cast(c_void_p(p_env_fns_int), POINTER(_lib.EnvFns))
+
+
+def wholememory_gather_op(wholememory_tensor, indices_tensor, output_tensor, p_env_fns_int, stream_int,
+                          gather_sms=-1):
+    _chk(lib.wholememory_gather(wholememory_tensor.wholememory_tensor, c_void_p(indices_tensor.get_c_handle()),
+                                c_void_p(output_tensor.get_c_handle()), _env_ptr(p_env_fns_int),
+                                c_void_p(stream_int), gather_sms))
+
+
+def wholememory_scatter_op(input_tensor, indices_tensor, wholememory_tensor, p_env_fns_int, stream_int,
+                           scatter_sms=-1):
+    _chk(lib.wholememory_scatter(c_void_p(input_tensor.get_c_handle()), c_void_p(indices_tensor.get_c_handle()),
+                                 wholememory_tensor.wholememory_tensor, _env_ptr(p_env_fns_int),
+                                 c_void_p(stream_int), scatter_sms))
+
+
+def csr_unweighted_sample_without_replacement(wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, center_nodes_tensor,
+                                              max_sample_count, output_sample_offset_tensor,
+                                              output_dest_memory_handle, output_center_localid_memory_handle,
+                                              output_edge_gid_memory_handle, random_seed, p_env_fns_int, stream_int):
+    _chk(lib.wholegraph_csr_unweighted_sample_without_replacement(
+        wm_csr_row_ptr_tensor.wholememory_tensor, wm_csr_col_ptr_tensor.wholememory_tensor,
+        c_void_p(center_nodes_tensor.get_c_handle()), max_sample_count,
+        c_void_p(output_sample_offset_tensor.get_c_handle()), c_void_p(output_dest_memory_handle),
+        c_void_p(output_center_localid_memory_handle), c_void_p(output_edge_gid_memory_handle), random_seed,
+        _env_ptr(p_env_fns_int), c_void_p(stream_int)))
+
+
+def host_generate_random_positive_int(random_seed, sub_sequence, output):
+    _chk(lib.generate_random_positive_int_cpu(random_seed, sub_sequence, c_void_p(output.get_c_handle())))
+
+
+# --------------------------------------------------------------------------- embedding
+class WholeMemoryOptimizer:
+    def __init__(self):
+        self.wm_optimizer = c_void_p(None)
+        self.optimizer_type = WholeMemoryOptimizerType.OptNone
+        self.param_dict = None
+
+    def create_optimizer(self, optimizer_type, param_dict):
+        self.optimizer_type = WholeMemoryOptimizerType(optimizer_type)
+        self.param_dict = param_dict
+        _chk(lib.wholememory_create_embedding_optimizer(byref(self.wm_optimizer), int(optimizer_type)))
+        for key, value in param_dict.items():
+            f = ctypes.c_float(float(value))
+            _chk(lib.wholememory_optimizer_set_parameter(self.wm_optimizer, key.encode("utf-8"),
+                                                         ctypes.cast(byref(f), c_void_p)))
+
+    def add_embedding(self, embedding):
+        _chk(lib.wholememory_embedding_set_optimizer(embedding.wm_embedding, self.wm_optimizer))
+
+    def destroy_optimizer(self):
+        if not self.wm_optimizer.value:
+            return
+        lib.wholememory_destroy_embedding_optimizer(self.wm_optimizer)
+        self.wm_optimizer = c_void_p(None)
+        self.optimizer_type = WholeMemoryOptimizerType.OptNone
+        self.param_dict = None
+
+
+def create_optimizer(optimizer_type, param_dict):
+    o = WholeMemoryOptimizer()
+    o.create_optimizer(optimizer_type, param_dict)
+    return o
+
+
+def create_non_optimizer():
+    return WholeMemoryOptimizer()
+
+
+class WholeMemoryCachePolicy:
+    def __init__(self):
+        self.cache_policy = c_void_p(None)
+
+    def create_policy(self, comm, memory_type, memory_location, access_type, ratio):
+        _chk(lib.wholememory_create_embedding_cache_policy(byref(self.cache_policy), comm.comm_id, int(memory_type),
+                                                           int(memory_location), int(access_type), ratio))
+
+    def destroy_policy(self):
+        if not self.cache_policy.value:
+            return
+        _chk(lib.wholememory_destroy_embedding_cache_policy(self.cache_policy))
+        self.cache_policy = c_void_p(None)
+
+
+def create_cache_policy(comm, memory_type, memory_location, access_type, ratio):
+    p = WholeMemoryCachePolicy()
+    p.create_policy(comm, memory_type, memory_location, access_type, ratio)
+    return p
+
+
+def create_non_cache_policy():
+    return WholeMemoryCachePolicy()
+
+
+class PyWholeMemoryEmbedding:
+    def __init__(self):
+        self.wm_embedding = c_void_p(None)
+
+    def create_embedding(self, tensor_desc, comm, memory_type, memory_location, cache_policy, embedding_entry_partition,
+                         user_defined_sms, round_robin_size):
+        part = None
+        if embedding_entry_partition is not None:
+            part = (c_size_t * len(embedding_entry_partition))(*embedding_entry_partition)
+        _chk(lib.wholememory_create_embedding(byref(self.wm_embedding), byref(tensor_desc.tensor_description),
+                                              comm.comm_id, int(memory_type), int(memory_location),
+                                              cache_policy.cache_policy, part, user_defined_sms, round_robin_size))
+
+    def destroy_embedding(self):
+        _chk(lib.wholememory_destroy_embedding(self.wm_embedding))
+        self.wm_embedding = c_void_p(None)
+
+    def writeback_all_cache(self, stream):
+        _chk(lib.wholememory_embedding_writeback_cache(self.wm_embedding, stream))
+
+    def drop_all_cache(self, stream):
+        _chk(lib.wholememory_embedding_drop_all_cache(self.wm_embedding, stream))
+
+    def get_embedding_tensor(self):
+        return PyWholeMemoryTensor(lib.wholememory_embedding_get_embedding_tensor(self.wm_embedding))
+
+    def get_optimizer_state_names(self):
+        names = lib.wholememory_embedding_get_optimizer_state_names(self.wm_embedding)
+        out, i = [], 0
+        while names and names[i] is not None:
+            out.append(names[i].decode("utf-8"))
+            i += 1
+        return out
+
+    def get_optimizer_state(self, state_name):
+        return PyWholeMemoryTensor(
+            lib.wholememory_embedding_get_optimizer_state(self.wm_embedding, state_name.encode("utf-8")))
+
+
+def create_embedding(tensor_desc, comm, memory_type, memory_location, cache_policy, embedding_entry_partition=None,
+                     user_defined_sms=-1, round_robin_size=0):
+    e = PyWholeMemoryEmbedding()
+    e.create_embedding(tensor_desc, comm, memory_type, memory_location, cache_policy, embedding_entry_partition,
+                       user_defined_sms, round_robin_size)
+    return e
+
+
+def EmbeddingGatherForward(wm_embedding, indice, output, adjust_cache, p_env_fns_int, stream_int):
+    _chk(lib.wholememory_embedding_gather(wm_embedding.wm_embedding, c_void_p(indice.get_c_handle()),
+                                          c_void_p(output.get_c_handle()), adjust_cache, _env_ptr(p_env_fns_int),
+                                          stream_int))
+
+
+def EmbeddingGatherGradientApply(wm_embedding, indice, grads, adjust_cache, lr, p_env_fns_int, stream_int):
+    _chk(lib.wholememory_embedding_gather_gradient_apply(wm_embedding.wm_embedding, c_void_p(indice.get_c_handle()),
+                                                         c_void_p(grads.get_c_handle()), adjust_cache, lr,
+                                                         _env_ptr(p_env_fns_int), stream_int))

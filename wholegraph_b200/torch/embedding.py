@@ -1,0 +1,223 @@
+"""WholeMemoryEmbedding / WholeMemoryOptimizer / WholeMemoryEmbeddingModule
+(mirror of pylibwholegraph/torch/embedding.py: optimizer :33-70, lookup autograd fn :213-243,
+embedding :246-377, create :380-470, module :537-555, optimizer factory :558-588).
+
+Cache policies exist as objects for API compatibility, but creating an embedding WITH one raises
+NotImplementedError (out of scope for an all-HBM B200 box)."""
+from typing import List, Union
+
+import torch
+
+from .. import binding as wmb
+from .comm import WholeMemoryCommunicator, get_global_communicator
+from .tensor import WholeMemoryTensor
+from .utils import (str_to_wmb_wholememory_access_type, str_to_wmb_wholememory_location,
+                    str_to_wmb_wholememory_memory_type, str_to_wmb_wholememory_optimizer_type,
+                    torch_dtype_to_wholememory_dtype)
+from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
+
+
+class WholeMemoryOptimizer(object):
+    """Sparse optimizer shared by any number of WholeMemoryEmbeddings; create with create_wholememory_optimizer."""
+
+    def __init__(self, global_comm: WholeMemoryCommunicator):
+        super().__init__()
+        self.wmb_opt = wmb.WholeMemoryOptimizer()
+        self.embeddings = []
+        self.global_comm = global_comm
+
+    def add_embedding(self, wm_embedding):
+        assert isinstance(wm_embedding, WholeMemoryEmbedding)
+        if wm_embedding.wmb_optimizer is not None:
+            raise ValueError("optimizer can only be set once.")
+        wm_embedding.wmb_optimizer = self.wmb_opt
+        wm_embedding.dummy_input.requires_grad_(True)
+        self.wmb_opt.add_embedding(wm_embedding.wmb_embedding)
+        self.embeddings.append(wm_embedding)
+
+    def step(self, lr: float):
+        """Apply the accumulated sparse gradients of every embedding, then barrier."""
+        for wm_embedding in self.embeddings:
+            if wm_embedding.need_apply:
+                wm_embedding.apply_gradients(lr)
+        self.global_comm.barrier()
+
+
+class WholeMemoryCachePolicy(object):
+    def __init__(self, wmb_cache_policy: wmb.WholeMemoryCachePolicy):
+        super().__init__()
+        self.wmb_cache_policy = wmb_cache_policy
+
+
+def create_wholememory_cache_policy(cache_comm: WholeMemoryCommunicator, *, memory_type: str = "chunked",
+                                    memory_location: str = "cuda", access_type: str = "readonly", ratio: float = 0.5):
+    p = wmb.WholeMemoryCachePolicy()
+    p.create_policy(cache_comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
+                    str_to_wmb_wholememory_location(memory_location), str_to_wmb_wholememory_access_type(access_type), ratio)
+    return WholeMemoryCachePolicy(p)
+
+
+def destroy_wholememory_cache_policy(cache_policy: WholeMemoryCachePolicy):
+    cache_policy.wmb_cache_policy.destroy_policy()
+    cache_policy.wmb_cache_policy = None
+
+
+class EmbeddingLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, indice: torch.Tensor, dummy_input: torch.Tensor, wm_embedding, is_training: bool = False,
+                force_dtype: Union[torch.dtype, None] = None):
+        output_tensor = wm_embedding.gather(indice, is_training=is_training, force_dtype=force_dtype)
+        if is_training and wm_embedding.need_grad():
+            ctx.save_for_backward(indice, output_tensor, dummy_input)
+            ctx.wm_embedding = wm_embedding
+        return output_tensor
+
+    @staticmethod
+    def backward(ctx, grad_outputs: torch.Tensor):
+        indice, output_tensor, dummy_input = ctx.saved_tensors
+        wm_embedding = ctx.wm_embedding
+        wm_embedding.add_gradients(indice, grad_outputs)
+        ctx.wm_embedding = None
+        return None, torch.zeros_like(dummy_input), None, None, None
+
+
+class WholeMemoryEmbedding(object):
+    r"""WholeMemory Embedding"""
+
+    def __init__(self, wmb_embedding: wmb.PyWholeMemoryEmbedding, wmb_cache_policy: Union[WholeMemoryCachePolicy, None]):
+        super().__init__()
+        self.wmb_embedding = wmb_embedding
+        self.embedding_tensor = None
+        self.optimizer_states = dict()
+        self.wmb_cache_policy = wmb_cache_policy
+        self.adjust_cache = self.wmb_cache_policy is not None
+        self.wmb_optimizer = None
+        self.dummy_input = torch.nn.Parameter(torch.zeros(1), requires_grad=False)
+        self.need_apply = False
+        self.sparse_indices = []
+        self.sparse_grads = []
+
+    def dim(self):
+        return self.get_embedding_tensor().dim()
+
+    @property
+    def shape(self):
+        return self.get_embedding_tensor().shape
+
+    def set_adjust_cache(self, adjust_cache: bool):
+        self.adjust_cache = adjust_cache if self.wmb_cache_policy is not None else False
+
+    def need_grad(self):
+        return self.wmb_optimizer is not None
+
+    def gather(self, indice: torch.Tensor, *, is_training: bool = False, force_dtype: Union[torch.dtype, None] = None):
+        assert indice.dim() == 1
+        embedding_dim = self.get_embedding_tensor().shape[1]
+        embedding_count = indice.shape[0]
+        current_cuda_device = "cuda:%d" % (torch.cuda.current_device(),)
+        output_dtype = force_dtype if force_dtype is not None else self.embedding_tensor.dtype
+        need_grad = self.need_grad() and is_training
+        output_tensor = torch.empty([embedding_count, embedding_dim], device=current_cuda_device, dtype=output_dtype,
+                                    requires_grad=need_grad)
+        if need_grad:
+            self.need_apply = True
+        wmb.EmbeddingGatherForward(self.wmb_embedding, wrap_torch_tensor(indice), wrap_torch_tensor(output_tensor),
+                                   self.adjust_cache, get_wholegraph_env_fns(), get_stream())
+        return output_tensor
+
+    def add_gradients(self, indice: torch.Tensor, grad_outputs: torch.Tensor):
+        self.sparse_indices.append(indice)
+        self.sparse_grads.append(grad_outputs)
+
+    def apply_gradients(self, lr: float):
+        sparse_indices = torch.cat(self.sparse_indices)
+        sparse_grads = torch.cat(self.sparse_grads)
+        wmb.EmbeddingGatherGradientApply(self.wmb_embedding, wrap_torch_tensor(sparse_indices),
+                                         wrap_torch_tensor(sparse_grads), self.adjust_cache, lr,
+                                         get_wholegraph_env_fns(), get_stream())
+        self.sparse_indices = []
+        self.sparse_grads = []
+        self.need_apply = False
+
+    def writeback_all_cache(self):
+        self.wmb_embedding.writeback_all_cache(get_stream())
+
+    def drop_all_cache(self):
+        self.wmb_embedding.drop_all_cache(get_stream())
+
+    def get_embedding_tensor(self):
+        if self.embedding_tensor is None:
+            self.embedding_tensor = WholeMemoryTensor(self.wmb_embedding.get_embedding_tensor())
+        return self.embedding_tensor
+
+    def get_optimizer_state_names(self):
+        return self.wmb_embedding.get_optimizer_state_names()
+
+    def get_optimizer_state(self, state_name):
+        if state_name not in self.optimizer_states:
+            self.optimizer_states[state_name] = WholeMemoryTensor(self.wmb_embedding.get_optimizer_state(state_name))
+        return self.optimizer_states[state_name]
+
+
+def create_embedding(comm: WholeMemoryCommunicator, memory_type: str, memory_location: str, dtype: torch.dtype,
+                     sizes: List[int], *, cache_policy: Union[WholeMemoryCachePolicy, None] = None,
+                     embedding_entry_partition: Union[List[int], None] = None, random_init: bool = False,
+                     gather_sms: int = -1, round_robin_size: int = 0):
+    """Create a [sizes[0], sizes[1]] embedding table row-sharded over comm."""
+    wmb_cache_policy = wmb.create_non_cache_policy() if cache_policy is None else cache_policy.wmb_cache_policy
+    assert len(sizes) == 2
+    tensor_desc = wmb.PyWholeMemoryTensorDescription()
+    tensor_desc.set_dtype(torch_dtype_to_wholememory_dtype(dtype))
+    tensor_desc.set_shape(sizes)
+    tensor_desc.set_stride([sizes[1], 1])
+    if embedding_entry_partition is not None and cache_policy is not None:
+        print("embedding_entry_partition is ignored because cache_policy is specified")
+        embedding_entry_partition = None
+    if embedding_entry_partition is not None and round_robin_size != 0:
+        print("round_robin_size is ignored because embedding_entry_partition is specified")
+        round_robin_size = 0
+    wm_embedding = WholeMemoryEmbedding(
+        wmb.create_embedding(tensor_desc, comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
+                             str_to_wmb_wholememory_location(memory_location), wmb_cache_policy,
+                             embedding_entry_partition=embedding_entry_partition, user_defined_sms=gather_sms,
+                             round_robin_size=round_robin_size),
+        cache_policy)
+    if random_init is True:
+        local_tensor, local_offset = wm_embedding.get_embedding_tensor().get_local_tensor()
+        torch.nn.init.xavier_uniform_(local_tensor)
+    comm.barrier()
+    return wm_embedding
+
+
+def destroy_embedding(wm_embedding: WholeMemoryEmbedding):
+    wm_embedding.wmb_embedding.destroy_embedding()
+    wm_embedding.wmb_embedding = None
+
+
+class WholeMemoryEmbeddingModule(torch.nn.Module):
+    """torch.nn.Module wrapper of WholeMemoryEmbedding."""
+
+    def __init__(self, wm_embedding: WholeMemoryEmbedding):
+        super().__init__()
+        self.wm_embedding = wm_embedding
+        self.embedding_gather_fn = EmbeddingLookupFn.apply
+
+    def forward(self, indice: torch.Tensor, force_dtype: Union[torch.dtype, None] = None):
+        return self.embedding_gather_fn(indice, self.wm_embedding.dummy_input, self.wm_embedding, self.training, force_dtype)
+
+
+def create_wholememory_optimizer(embeddings: Union[WholeMemoryEmbedding, List[WholeMemoryEmbedding]], optimizer_type: str,
+                                 param_dict: dict, global_comm: Union[WholeMemoryCommunicator, None] = None):
+    wm_optimizer = WholeMemoryOptimizer(global_comm if global_comm is not None else get_global_communicator())
+    wm_optimizer.wmb_opt.create_optimizer(str_to_wmb_wholememory_optimizer_type(optimizer_type), param_dict)
+    if isinstance(embeddings, WholeMemoryEmbedding):
+        wm_optimizer.add_embedding(embeddings)
+    else:
+        for em in embeddings:
+            wm_optimizer.add_embedding(em)
+    return wm_optimizer
+
+
+def destroy_wholememory_optimizer(optimizer: WholeMemoryOptimizer):
+    optimizer.wmb_opt.destroy_optimizer()
+    optimizer.wmb_opt = None
