@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--memory-type", default=None, choices=[None, "continuous", "chunked", "distributed"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--index-pattern", default="random", choices=["random", "sequential"], help="diagnostic; the metric is 'random'")
+    p.add_argument("--per-step-events", action="store_true", help="diagnostic: also time every step with its own event pair")
     return p.parse_args()
 
 
@@ -184,6 +186,8 @@ def main():
     gen.manual_seed(0x5EED + rank)
     n_batches = 8  # distinct index batches, cycled: successive steps never re-read the same rows
     idx_dev = [torch.randint(0, rows_total, (n,), device="cuda", dtype=torch.int64, generator=gen) for _ in range(n_batches)]
+    if args.index_pattern == "sequential":  # diagnostic only: contiguous rows = the kernel's ceiling without DRAM page misses
+        idx_dev = [(torch.arange(n, device="cuda", dtype=torch.int64) + (b * n * 7) % max(1, rows_total - n)) for b in range(n_batches)]
     out = torch.empty(n, dim, device="cuda", dtype=th_dtype)
     env = get_wholegraph_env_fns()
     stream = torch.cuda.current_stream()
@@ -227,6 +231,15 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.summary() if sampler else None
 
+    if args.per_step_events and rank == 0:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i, (a, b) in enumerate(evs):
+            a.record(stream)
+            step(i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        per = sorted(a.elapsed_time(b) for a, b in evs)
+        print("per-step kernel ms: min %.4f median %.4f max %.4f (loop mean %.4f)" % (per[0], per[len(per) // 2], per[-1], ms), file=sys.stderr)
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)

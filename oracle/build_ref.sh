@@ -1,0 +1,58 @@
+#!/usr/bin/env bash
+# Builds the REFERENCE's own gather/scatter path (rapidsai/wholegraph, unmodified sources where they lie under
+# /root/reference) for sm_100 into oracle/_ref/libwholegraph_ref.so -- test infrastructure: the bit-exact GPU
+# oracle and the "reference arm" of bench.py.  No reference source is copied into the repo; only objects and the
+# .so are written, under the git-ignored oracle/_ref/.  The reference's cmake build needs network (rapids-cmake,
+# RAFT via CPM), so the few translation units on the path are compiled directly with a ~70-line RAFT shim
+# (oracle/ref_shim) -- recipe from SURVEY.md Appendix B.  Embedding/optimizer/sampling TUs need real RAFT headers
+# and are NOT built.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF_ROOT:-/root/reference}"
+OUT="$HERE/_ref"
+OBJ="$OUT/obj"
+[ -d "$REF/cpp/src" ] || { echo "no reference tree at $REF"; exit 3; }
+if [ -f "$OUT/libwholegraph_ref.so" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_stubs.cpp" ]; then
+  echo "oracle/_ref/libwholegraph_ref.so is up to date"; exit 0
+fi
+mkdir -p "$OBJ"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+INC="-I$REF/cpp/include -I$REF/cpp/src -I$HERE/ref_shim -I/usr/include -I/usr/local/cuda/include"
+NVFLAGS="-std=c++17 -O3 -gencode arch=compute_100,code=sm_100 -Xcompiler -fPIC -w $INC"
+CXXFLAGS="-std=c++17 -O2 -fPIC -w $INC"
+S="$REF/cpp/src"
+CPP="cuda_macros.cpp logger.cpp
+ wholememory/communicator.cpp wholememory/nccl_comms.cpp wholememory/memory_handle.cpp wholememory/wholememory.cpp
+ wholememory/wholememory_tensor.cpp wholememory/tensor_description.cpp wholememory/env_func_ptrs.cpp
+ wholememory/initialize.cpp wholememory/system_info.cpp wholememory/global_reference.cpp
+ wholememory_ops/gather_op.cpp wholememory_ops/scatter_op.cpp wholememory_ops/thrust_allocator.cpp"
+CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl.cu
+ wholememory_ops/scatter_op_impl_mapped.cu wholememory_ops/scatter_op_impl_nccl.cu
+ wholememory_ops/functions/gather_func.cu wholememory_ops/functions/scatter_func.cu
+ wholememory_ops/functions/bucket_ids_func.cu wholememory_ops/functions/exchange_ids_nccl_func.cu
+ wholememory_ops/functions/exchange_embeddings_nccl_func.cu wholememory_ops/functions/sort_indices_func.cu
+ wholememory_ops/functions/gather_func_impl_floating_data_int32_indices.cu
+ wholememory_ops/functions/gather_func_impl_floating_data_int64_indices.cu
+ wholememory_ops/functions/gather_func_impl_integer_data_int32_indices.cu
+ wholememory_ops/functions/gather_func_impl_integer_data_int64_indices.cu
+ wholememory_ops/functions/scatter_func_impl_floating_data_int32_indices.cu
+ wholememory_ops/functions/scatter_func_impl_floating_data_int64_indices.cu
+ wholememory_ops/functions/scatter_func_impl_integer_data_int32_indices.cu
+ wholememory_ops/functions/scatter_func_impl_integer_data_int64_indices.cu"
+MK="$OBJ/Makefile"
+{
+  echo "all: objs"
+  OBJS=""
+  for f in $CPP; do o="$OBJ/$(echo "$f" | tr '/' '_').o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$S/$f" "$CXXFLAGS"; done
+  for f in $CU; do o="$OBJ/$(echo "$f" | tr '/' '_').o"; OBJS="$OBJS $o"; printf '%s: %s\n\t%s %s -c $< -o $@\n' "$o" "$S/$f" "$NVCC" "$NVFLAGS"; done
+  o="$OBJ/ref_stubs.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_stubs.cpp" "$CXXFLAGS"
+  echo "objs:$OBJS"
+  echo "OBJS=$OBJS"
+} > "$MK"
+make -f "$MK" -j"$(nproc)" objs
+OBJS=$(grep '^OBJS=' "$MK" | cut -d= -f2-)
+# libnvidia-ml: the reference probes GPU fabric info through NVML at communicator creation (system_info.cpp:139-154)
+NVML="-lnvidia-ml"
+[ -e /usr/lib/x86_64-linux-gnu/libnvidia-ml.so.1 ] || NVML="-L/usr/local/cuda/lib64/stubs -lnvidia-ml"
+$NVCC -shared -gencode arch=compute_100,code=sm_100 -o "$OUT/libwholegraph_ref.so" $OBJS -lcuda -lnccl $NVML -L/usr/local/cuda/lib64/stubs -ldl -lpthread
+echo "built $OUT/libwholegraph_ref.so"

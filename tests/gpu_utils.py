@@ -27,13 +27,23 @@ def single_comm():
 
 def np_to_torch(a, dt):
     """numpy array (bf16 as uint16 bits) -> torch tensor of the real dtype, on the host."""
+    if a.size == 0:  # from_numpy of an empty array reports zero strides; build it natively instead
+        return torch.empty(a.shape, dtype=TORCH_OF[dt])
     t = torch.from_numpy(np.ascontiguousarray(a))
     return t.view(torch.bfloat16) if dt == O.DT_BF16 else t
 
 
 def torch_to_np(t, dt):
-    t = t.detach().cpu().contiguous()
+    t = t.detach().cpu().contiguous().clone()  # clone: host WholeMemory views alias memory that is unmapped on destroy
     return t.view(torch.int16).numpy().view(np.uint16) if dt == O.DT_BF16 else t.numpy()
+
+
+def idx_to_cuda(idx_np):
+    """numpy index array -> cuda tensor; an EMPTY from_numpy tensor reports stride 0, which the C ABI (like the
+    reference's) rejects for 1-D arrays, so empty batches are created natively."""
+    if idx_np.shape[0] == 0:
+        return torch.empty(0, dtype=torch.int64 if idx_np.dtype == np.int64 else torch.int32, device="cuda")
+    return torch.from_numpy(idx_np).cuda()
 
 
 def random_table(rng, dt, rows, stride):

@@ -1,0 +1,202 @@
+"""Multi-rank GPU scenarios run by test_multi_rank_gpu.py (one spawned process per rank).
+
+Every rank rebuilds the SAME host-side model of the whole table from a shared seed, performs its part through the
+C ABI, and checks what it can see against the oracle.  Ranks may share one GPU (VMM mappings work across
+processes on the same device); scenarios that need NCCL require one GPU per rank."""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _setup(rank, world, port, ngpus, env):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(env)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import wholegraph_b200.torch as wgth
+    torch.cuda.set_device(rank % ngpus)
+    # gloo process group: only used to broadcast the unique id (ranks may share a GPU, which NCCL refuses)
+    wgth.init_torch_env(rank, world, rank % ngpus, world, wm_log_level="warn", backend="gloo")
+    torch.cuda.set_device(rank % ngpus)
+    return wgth.get_global_communicator()
+
+
+def _random_partition(rng, rows, world):
+    cuts = np.sort(rng.choice(np.arange(1, rows), size=world - 1, replace=False))
+    return np.diff(np.concatenate([[0], cuts, [rows]])).astype(np.int64).tolist()
+
+
+def scenario_gather_scatter(rank, world, comm):
+    import torch
+    import gpu_utils as G
+    import wholegraph_b200.binding as wmb
+    from oracle import oracle as O
+    dev = torch.cuda.current_device()
+    cases = [("continuous", "cuda", O.DT_FLOAT, O.DT_FLOAT, 128, 128, False), ("chunked", "cuda", O.DT_HALF, O.DT_HALF, 128, 128, False),
+             ("chunked", "cuda", O.DT_FLOAT, O.DT_HALF, 33, 36, True), ("distributed", "cuda", O.DT_FLOAT, O.DT_FLOAT, 64, 64, False),
+             ("distributed", "cuda", O.DT_INT64, O.DT_INT, 7, 8, True), ("continuous", "cpu", O.DT_FLOAT, O.DT_FLOAT, 32, 32, False),
+             ("chunked", "cpu", O.DT_HALF, O.DT_FLOAT, 11, 12, True), ("continuous", "cuda", O.DT_DOUBLE, O.DT_DOUBLE, 5, 5, True)]
+    rows = 10007
+    for ci, (mt, loc, tab_dt, out_dt, cols, stride, custom) in enumerate(cases):
+        rng = np.random.default_rng(1000 + ci)  # same stream on every rank
+        part = _random_partition(rng, rows, world) if custom else None
+        host = G.random_table(rng, tab_dt, rows, stride)
+        t = wmb.create_wholememory_matrix(G.WM_OF[tab_dt], rows, cols, stride, comm.wmb_comm, G.MT[mt], G.ML[loc], part)
+        view_loc = wmb.MlDevice if loc == "cuda" else wmb.MlHost
+        local, first = t.get_wholememory_handle().get_local_flatten_tensor(G.WM_OF[tab_dt], view_loc, dev)
+        first_row = first // stride
+        nloc = local.numel() // stride
+        offs = t.get_entry_offsets()
+        assert offs[rank] == first_row and offs[rank + 1] - offs[rank] == nloc and offs[-1] == rows, (offs, first_row, nloc)
+        if part is not None:
+            assert np.diff(offs).tolist() == part
+        local.reshape(nloc, stride).copy_(G.np_to_torch(host[first_row:first_row + nloc], tab_dt))
+        comm.barrier()
+        rrng = np.random.default_rng(77 * ci + rank)
+        idx = rrng.integers(0, rows, size=3000 + rank).astype(np.int64 if ci % 2 == 0 else np.int32)
+        idx[::131] = -1
+        n = idx.shape[0]
+        sentinel = G.random_table(rrng, out_dt, n, cols)
+        out_t = G.np_to_torch(sentinel.copy(), out_dt).cuda()
+        G.gather(t, torch.from_numpy(idx).cuda(), out_t)
+        torch.cuda.synchronize()
+        exp = sentinel.copy()
+        O.gather(host, tab_dt, idx, out_dt, out=exp, cols=cols)
+        assert G.torch_to_np(out_t, out_dt).tobytes() == exp.tobytes(), f"gather mismatch case {ci} rank {rank}"
+        comm.barrier()
+        # scatter: rank r owns target rows r, r+world, ... (disjoint across ranks), input in the OUT dtype family
+        target = np.arange(rank, rows, world)
+        sel = rrng.permutation(target)[:1500].astype(np.int64)
+        src = G.random_table(np.random.default_rng(5000 + ci * 16 + rank), out_dt, sel.shape[0], cols)
+        G.scatter(G.np_to_torch(src, out_dt).cuda(), torch.from_numpy(sel).cuda(), t)
+        comm.barrier()
+        for r in range(world):  # replay every rank's scatter on the host model
+            tr = np.arange(r, rows, world)
+            rr = np.random.default_rng(77 * ci + r)
+            rr.integers(0, rows, size=3000 + r)
+            G.random_table(rr, out_dt, 3000 + r, cols)
+            s_r = rr.permutation(tr)[:1500].astype(np.int64)
+            src_r = G.random_table(np.random.default_rng(5000 + ci * 16 + r), out_dt, s_r.shape[0], cols)
+            O.scatter(src_r, out_dt, s_r, host, tab_dt, cols=cols)
+        got = G.torch_to_np(local.reshape(nloc, stride), tab_dt)
+        assert got.tobytes() == host[first_row:first_row + nloc].tobytes(), f"scatter mismatch case {ci} rank {rank}"
+        # and through a remote gather of everything
+        all_idx = np.arange(rows, dtype=np.int64)
+        full = torch.empty(rows, cols, dtype=G.TORCH_OF[tab_dt], device="cuda")
+        G.gather(t, torch.from_numpy(all_idx).cuda(), full)
+        torch.cuda.synchronize()
+        assert G.torch_to_np(full, tab_dt).tobytes() == np.ascontiguousarray(host[:, :cols]).tobytes(), f"full gather case {ci}"
+        comm.barrier()
+        wmb.destroy_wholememory_tensor(t)
+
+
+def scenario_gradient(rank, world, comm):
+    import torch
+    import wholegraph_b200.torch as wgth
+    from oracle import oracle as O
+    cfgs = [("adam", {}, "chunked", 392), ("adam", {"adam_w": 1.0, "weight_decay": 0.01}, "distributed", 127),
+            ("sgd", {"weight_decay": 0.02}, "continuous", 4), ("adagrad", {"epsilon": 1e-6}, "distributed", 129),
+            ("rmsprop", {"alpha": 0.9}, "chunked", 3)]
+    rows = 5000
+    for ci, (kind, params, mt, dim) in enumerate(cfgs):
+        rng = np.random.default_rng(300 + ci)
+        w = rng.standard_normal((rows, dim)).astype(np.float32)
+        emb = wgth.create_embedding(comm, mt, "cuda", torch.float32, [rows, dim])
+        opt = wgth.create_wholememory_optimizer(emb, kind, params, global_comm=comm)
+        local, first_row = emb.get_embedding_tensor().get_local_tensor()
+        local.copy_(torch.from_numpy(w[first_row:first_row + local.shape[0]]))
+        comm.barrier()
+        m = np.zeros_like(w)
+        v = np.zeros_like(w)
+        b12 = np.ones((rows, 2), np.float32)
+        for step in range(3):
+            all_idx, all_g = [], []
+            for r in range(world):
+                rr = np.random.default_rng(9000 + ci * 100 + step * 10 + r)
+                n = 700 + 13 * r
+                idx_r = (rr.zipf(1.3, size=n) % rows).astype(np.int64)  # heavy duplication
+                g_r = rr.standard_normal((n, dim)).astype(np.float32)
+                all_idx.append(idx_r)
+                all_g.append(g_r)
+            emb.add_gradients(torch.from_numpy(all_idx[rank]).cuda(), torch.from_numpy(all_g[rank]).cuda())
+            emb.need_apply = True
+            opt.step(0.01)
+            urows, ug = O.dedup_gradients(np.concatenate(all_idx), np.concatenate(all_g))
+            kw = dict(weight_decay=params.get("weight_decay", 0.0), epsilon=params.get("epsilon", 1e-8))
+            if kind == "adam":
+                O.optimizer_step("adam", w, urows, ug, 0.01, state=(m, v), b12=b12, adam_w=params.get("adam_w", 0) > 0.5, **kw)
+            elif kind == "sgd":
+                O.optimizer_step("sgd", w, urows, ug, 0.01, weight_decay=kw["weight_decay"])
+            elif kind == "adagrad":
+                O.optimizer_step("adagrad", w, urows, ug, 0.01, state=m, **kw)
+            else:
+                O.optimizer_step("rmsprop", w, urows, ug, 0.01, state=m, alpha=params.get("alpha", 0.99), **kw)
+        torch.cuda.synchronize()
+        got = local.cpu().numpy()
+        exp = w[first_row:first_row + local.shape[0]]
+        assert np.allclose(got, exp, rtol=1e-5, atol=1e-5), f"{kind} mismatch: max abs {np.abs(got - exp).max()}"
+        names = emb.get_optimizer_state_names()
+        assert names == {"adam": ["m", "v", "beta12t"], "sgd": [], "adagrad": ["state_sum"], "rmsprop": ["v"]}[kind]
+        if kind == "adam":
+            ml, mfirst = emb.get_optimizer_state("m").get_local_tensor()
+            assert np.allclose(ml.cpu().numpy(), m[mfirst:mfirst + ml.shape[0]], rtol=1e-5, atol=1e-6)
+        comm.barrier()
+        wgth.destroy_wholememory_optimizer(opt)
+        wgth.destroy_embedding(emb)
+
+
+def scenario_sampling(rank, world, comm):
+    import torch
+    import wholegraph_b200.binding as wmb
+    import wholegraph_b200.torch as wgth
+    from oracle import oracle as O
+    rng = np.random.default_rng(42)
+    nodes = 4000
+    deg = np.minimum(rng.zipf(1.5, size=nodes), 400) + rng.integers(0, 12, size=nodes)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    for col_dtype, wm_col, th_col in [(np.int64, wmb.DtInt64, torch.int64), (np.int32, wmb.DtInt, torch.int32)]:
+        col = rng.integers(0, nodes, size=int(row_ptr[-1])).astype(col_dtype)
+        for mt in (wmb.MtChunked, wmb.MtContinuous, wmb.MtDistributed):
+            rp = wmb.create_wholememory_array(wmb.DtInt64, nodes + 1, comm.wmb_comm, mt, wmb.MlDevice)
+            cp = wmb.create_wholememory_array(wm_col, col.size, comm.wmb_comm, mt, wmb.MlDevice)
+            for t, host, dt in ((rp, row_ptr, wmb.DtInt64), (cp, col, wm_col)):
+                loc, first = t.get_wholememory_handle().get_local_flatten_tensor(dt, wmb.MlDevice, torch.cuda.current_device())
+                loc.copy_(torch.from_numpy(host[first:first + loc.numel()]))
+            comm.barrier()
+            crng = np.random.default_rng(7 + rank)
+            for k, cdt in [(10, np.int64), (25, np.int32), (32, np.int64), (40, np.int64), (100, np.int32), (-1, np.int64)]:
+                centers = crng.integers(0, nodes, size=257).astype(cdt)
+                seed = 1234 + k
+                res = wgth.unweighted_sample_without_replacement(rp, cp, torch.from_numpy(centers).cuda(), k, random_seed=seed,
+                                                                 need_center_local_output=True, need_edge_output=True)
+                eo, ed, el, eg = O.unweighted_sample(row_ptr, col.astype(np.int64), centers.astype(np.int64), k, seed)
+                assert res[0].cpu().numpy().tolist() == eo.tolist(), f"offsets k={k}"
+                assert res[1].dtype == th_col and res[1].cpu().numpy().astype(np.int64).tolist() == ed.tolist(), f"dst k={k}"
+                assert res[2].cpu().numpy().tolist() == el.tolist() and res[3].cpu().numpy().tolist() == eg.tolist(), f"ids k={k}"
+            comm.barrier()
+            wmb.destroy_wholememory_tensor(rp)
+            wmb.destroy_wholememory_tensor(cp)
+
+
+SCENARIOS = {"gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+
+
+def worker(rank, world, port, ngpus, scenario, env, results):
+    try:
+        comm = _setup(rank, world, port, ngpus, env)
+        SCENARIOS[scenario](rank, world, comm)
+        results[rank] = "ok"
+    except Exception:
+        results[rank] = "FAIL: " + traceback.format_exc()
+    finally:
+        try:
+            import wholegraph_b200.torch as wgth
+            wgth.finalize()
+        except Exception:
+            pass

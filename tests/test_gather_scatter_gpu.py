@@ -37,7 +37,7 @@ def _check_gather(G, mem_type, location, tab_dt, out_dt, idx_np, rows, cols, str
     out_stride = cols if out_stride is None else out_stride
     sentinel = G.random_table(rng, out_dt, max(n, 1), out_stride)[:n]
     out_t = G.np_to_torch(sentinel.copy(), out_dt).cuda()
-    idx_t = torch.from_numpy(idx_np).cuda()
+    idx_t = G.idx_to_cuda(idx_np)
     G.gather(table, idx_t, out_t[:, :cols] if out_stride != cols else out_t, sms)
     torch.cuda.synchronize()
     got = G.torch_to_np(out_t, out_dt)

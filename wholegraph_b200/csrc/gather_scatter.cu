@@ -23,10 +23,31 @@ inline int pow2_divisor(uint64_t v, int cap)
   return a;
 }
 
+/* developer knobs for sweeps on the GPU box (unset in production): WG_UNROLL, WG_BATCH_ROWS, WG_BLOCKS_PER_SM */
+int env_int(const char* name, int dflt)
+{
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+int tuned_unroll()
+{
+  static const int u = env_int("WG_UNROLL", kUnroll);
+  return u;
+}
+
 template <typename IdxT, int VEC, bool GATHER>
 void launch_vec(const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
 {
-  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, kThreads, 0, s>>>(t, g, static_cast<const IdxT*>(idx), n, dense);
+  const IdxT* ip = static_cast<const IdxT*>(idx);
+  if constexpr (VEC == 16) {
+    /* the 16-byte path is the hot one: loads-in-flight per lane is tunable */
+    switch (tuned_unroll()) {
+      case 2: row_move_vec_kernel<IdxT, VEC, GATHER, 2><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense); return;
+      case 8: row_move_vec_kernel<IdxT, VEC, GATHER, 8><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense); return;
+      default: break;
+    }
+  }
+  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense);
 }
 
 template <typename IdxT, bool GATHER>
@@ -45,10 +66,17 @@ int vec_blocks_per_sm()
 {
   static int occ = [] {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, kUnroll>, kThreads, 0) != cudaSuccess || o <= 0) {
+    cudaError_t e;
+    switch (tuned_unroll()) {
+      case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, 2>, kThreads, 0); break;
+      case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, 8>, kThreads, 0); break;
+      default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, kUnroll>, kThreads, 0); break;
+    }
+    if (e != cudaSuccess || o <= 0) {
       (void)cudaGetLastError();
       o = 4;
     }
+    o = env_int("WG_BLOCKS_PER_SM", o);
     return o;
   }();
   return occ;
@@ -65,6 +93,8 @@ void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_r
   int R               = 32;
   while (R > 1 && (int64_t)R * row_bytes > 16384) R >>= 1;
   while (R > 1 && n / R < total_warps * 4) R >>= 1;
+  static const int forced_rows = env_int("WG_BATCH_ROWS", 0);
+  if (forced_rows > 0) R = forced_rows;
   int64_t nbatch = (n + R - 1) / R;
   int64_t need   = (nbatch + (kThreads / 32) - 1) / (kThreads / 32);
   *batch_rows    = R;

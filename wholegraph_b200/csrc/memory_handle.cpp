@@ -87,6 +87,14 @@ void vmm_create(wholememory_handle_t h, bool map_peers)
   WM_CUDA(cudaSetDevice(c->dev_id));
   h->backing   = wholememory_handle_::backing_t::vmm;
   h->page_size = c->alloc_granularity;
+  /* Mapping granule.  Large tables are laid out in 512 MiB-aligned granules (as the reference does for
+   * totals >= 16 GiB, memory_handle.cpp:229-230,1686-1687) so the driver can use its largest page size
+   * and random row reads miss the TLB less.  WG_VMM_PAGE_MB overrides (developer knob). */
+  {
+    const char* v   = getenv("WG_VMM_PAGE_MB");
+    size_t want     = (v && *v) ? (size_t)atol(v) << 20 : (h->total_size >= ((size_t)16 << 30) ? (size_t)512 << 20 : 0);
+    if (want > h->page_size) h->page_size = round_up(want, c->alloc_granularity);
+  }
   h->map_offsets.assign(ws, 0);
   h->map_sizes.assign(ws, 0);
   h->phys.assign(ws, 0);

@@ -12,7 +12,17 @@
 
 namespace wm {
 
-bool handle_is_addressable(wholememory_handle_t h) { return h->peer_mapped; }
+bool handle_is_addressable(wholememory_handle_t h)
+{
+  /* WG_FORCE_EXCHANGE=1: route DISTRIBUTED ops through the NCCL bucket exchange even when the shards
+   * are peer-mapped (exercises the no-NVLink path on an NVSwitch box and on 1 rank) */
+  static const bool force_exchange = [] {
+    const char* v = getenv("WG_FORCE_EXCHANGE");
+    return v != nullptr && v[0] != '\0' && v[0] != '0';
+  }();
+  if (force_exchange && h->type == WHOLEMEMORY_MT_DISTRIBUTED) return false;
+  return h->peer_mapped;
+}
 
 table_ref make_table_ref(wholememory_tensor_t t)
 {
