@@ -84,6 +84,15 @@ int vec_blocks_per_sm()
 
 /* rows per warp batch + grid size.  Enough batches to balance the persistent grid, small enough
  * batches that one warp does not serialise a long copy. */
+/* magic multiplier for floor(w / d) = (w * magic) >> 40, exact while w < 2^20 and d < 2^20 */
+void set_units(row_geom* g, int64_t units_per_row)
+{
+  WM_EXPECT(units_per_row > 0 && units_per_row * 32 < (1 << 20), WHOLEMEMORY_NOT_SUPPORTED,
+            "row too long for the gather/scatter kernels (%ld units)", (long)units_per_row);
+  g->units_per_row = (int)units_per_row;
+  g->div_magic     = (((uint64_t)1 << 40) + (uint64_t)units_per_row - 1) / (uint64_t)units_per_row;
+}
+
 void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_rows, int* grid)
 {
   int total_sms = sm_count();
@@ -150,6 +159,8 @@ void row_move(bool gather,
   g.table_offset_bytes = td.storage_offset * et;
   g.table_stride_bytes = td.stride * et;
   g.dense_stride_bytes = dd.stride * ed;
+  static const int cache_policy = env_int("WG_CACHE_POLICY", 0);
+  g.policy                      = cache_policy;
 
   /* alignment shared by both sides, in bytes of each side's element */
   uint64_t t_bits = (uint64_t)g.table_offset_bytes | (uint64_t)g.table_stride_bytes;
@@ -159,7 +170,8 @@ void row_move(bool gather,
   if (td.dtype == dd.dtype) {
     const int64_t row_bytes = td.sizes[1] * et;
     int vec                 = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, 16);
-    g.row_elems             = (int)(row_bytes / vec);
+    g.row_elems             = (int)td.sizes[1];
+    set_units(&g, row_bytes / vec);
     int grid                = 1;
     plan(n, row_bytes, sms, vec_blocks_per_sm(), &g.batch_rows, &grid);
     if (gather) {
@@ -177,6 +189,7 @@ void row_move(bool gather,
     /* t_bits/d_bits are multiples of the element size by construction of the descriptors */
     int align = std::min(a_t, a_d);
     g.row_elems = (int)td.sizes[1];
+    set_units(&g, td.sizes[1] / align);
     int grid    = 1;
     plan(n, td.sizes[1] * std::max(et, ed), sms, cvt_blocks_per_sm(), &g.batch_rows, &grid);
     cvt_launch_fn fn = t_float ? find_float_cvt(td.dtype, dd.dtype) : find_int_cvt(td.dtype, dd.dtype);

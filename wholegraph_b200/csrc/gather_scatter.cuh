@@ -107,6 +107,30 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p)
 __device__ __forceinline__ uint16_t ld_stream(const uint16_t* p) { return *p; }
 __device__ __forceinline__ uint8_t ld_stream(const uint8_t* p) { return *p; }
 
+/* experiment variants of the 16-byte accesses, selected by row_geom::policy (warp-uniform) */
+__device__ __forceinline__ uint4 ld_variant(const uint4* p, int variant)
+{
+  uint4 v;
+  switch (variant) {
+    case 1: asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); break;
+    case 2: asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); break;
+    case 3: asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); break;
+    case 4: asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); break;
+    default: asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); break;
+  }
+  return v;
+}
+__device__ __forceinline__ void st_variant(uint4* p, uint4 v, int variant)
+{
+  switch (variant) {
+    case 1: asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); break;
+    case 2: asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); break;
+    case 3: asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); break;
+    case 4: asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); break;
+    default: asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); break;
+  }
+}
+
 /* write-once data: evict-first so it does not push table lines out of L2 */
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v)
 {
@@ -153,9 +177,8 @@ __global__ void __launch_bounds__(256) row_move_vec_kernel(table_ref tref,
   const int64_t nwarps = (int64_t)gridDim.x * warps_cta;
   const int R          = g.batch_rows;
   const int64_t nbatch = (n + R - 1) / R;
-  const uint32_t Vn    = (uint32_t)g.row_elems; /* vec kernels: host passes the row size in VEC units */
-  const bool pow2      = (Vn & (Vn - 1)) == 0;
-  const int shift      = 31 - __clz(Vn);
+  const uint32_t Vn    = (uint32_t)g.units_per_row; /* row size in VEC units */
+  const uint64_t magic = g.div_magic;
 
   int64_t batch = warp;
   /* software prefetch of the next batch's index */
@@ -187,7 +210,7 @@ __global__ void __launch_bounds__(256) row_move_vec_kernel(table_ref tref,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         uint32_t w   = w0 + (uint32_t)u * 32u + (uint32_t)lane;
-        uint32_t row = pow2 ? (w >> shift) : (w / Vn);
+        uint32_t row = (uint32_t)(((uint64_t)w * magic) >> 40);
         uint32_t v   = w - row * Vn;
         /* shuffles are executed by all lanes, out-of-range lanes read lane (row & 31) harmlessly */
         char* t   = shfl_ptr(trow, (int)(row & 31u));
@@ -197,7 +220,8 @@ __global__ void __launch_bounds__(256) row_move_vec_kernel(table_ref tref,
         dst[u]    = nullptr;
         if (live) {
           if (GATHER) {
-            val[u] = ld_stream(reinterpret_cast<const V*>(tp));
+            if constexpr (VEC == 16) val[u] = ld_variant(reinterpret_cast<const uint4*>(tp), g.policy & 15);
+            else val[u] = ld_stream(reinterpret_cast<const V*>(tp));
             dst[u] = dp;
           } else {
             val[u] = ld_stream(reinterpret_cast<const V*>(dp));
@@ -208,9 +232,10 @@ __global__ void __launch_bounds__(256) row_move_vec_kernel(table_ref tref,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (dst[u] != nullptr) {
-          if (GATHER)
-            st_stream(reinterpret_cast<V*>(dst[u]), val[u]);
-          else
+          if (GATHER) {
+            if constexpr (VEC == 16) st_variant(reinterpret_cast<uint4*>(dst[u]), val[u], g.policy >> 4);
+            else st_stream(reinterpret_cast<V*>(dst[u]), val[u]);
+          } else
             *reinterpret_cast<V*>(dst[u]) = val[u];
         }
       }
@@ -264,7 +289,8 @@ __global__ void __launch_bounds__(256) row_move_cvt_kernel(table_ref tref,
   const int64_t nwarps = (int64_t)gridDim.x * warps_cta;
   const int R          = g.batch_rows;
   const int64_t nbatch = (n + R - 1) / R;
-  const uint32_t Vn    = (uint32_t)g.row_elems / ALIGN; /* packs per row */
+  const uint32_t Vn    = (uint32_t)g.units_per_row; /* ALIGN-element packs per row */
+  const uint64_t magic = g.div_magic;
 
   for (int64_t batch = warp; batch < nbatch; batch += nwarps) {
     const int64_t first = batch * R;
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(256) row_move_cvt_kernel(table_ref tref,
     const uint32_t total = (uint32_t)R * Vn;
     for (uint32_t w0 = 0; w0 < total; w0 += 32u) {
       uint32_t w   = w0 + (uint32_t)lane;
-      uint32_t row = w / Vn;
+      uint32_t row = (uint32_t)(((uint64_t)w * magic) >> 40);
       uint32_t v   = w - row * Vn;
       char* t      = shfl_ptr(trow, (int)(row & 31u));
       if (w < total && t != nullptr) {

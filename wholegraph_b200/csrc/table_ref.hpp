@@ -25,6 +25,11 @@ struct row_geom {
   int64_t dense_stride_bytes;
   int row_elems;   /* columns */
   int batch_rows;  /* rows resolved per warp batch: power of two <= 32 */
+  /* division-free "unit index -> (row, unit in row)": row = (w * div_magic) >> 40, exact for w, units < 2^20.
+   * (an integer divide per vector runs on the XU pipe and was measured to saturate it at 96 %) */
+  uint64_t div_magic;
+  int units_per_row; /* vectors (copy kernels) or ALIGN-packs (converting kernels) per row */
+  int policy;        /* developer knob (WG_CACHE_POLICY): load variant | store variant << 4; 0 = default */
 };
 
 }  // namespace wm
