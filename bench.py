@@ -50,7 +50,8 @@ def parse():
     p.add_argument("--memory-type", default=None, choices=[None, "continuous", "chunked", "distributed"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--index-pattern", default="random", choices=["random", "sequential"], help="diagnostic; the metric is 'random'")
+    p.add_argument("--index-pattern", default="random", choices=["random", "sequential", "remote", "local"],
+                   help="diagnostic; the metric is 'random' (uniform over the whole table)")
     p.add_argument("--per-step-events", action="store_true", help="diagnostic: also time every step with its own event pair")
     return p.parse_args()
 
@@ -186,6 +187,16 @@ def main():
     gen.manual_seed(0x5EED + rank)
     n_batches = 8  # distinct index batches, cycled: successive steps never re-read the same rows
     idx_dev = [torch.randint(0, rows_total, (n,), device="cuda", dtype=torch.int64, generator=gen) for _ in range(n_batches)]
+    if args.index_pattern in ("remote", "local") and world > 1:  # diagnostic: only peer rows / only my rows
+        per = args.rows_per_gpu
+        idx_dev = []
+        for _ in range(n_batches):
+            r = torch.randint(0, per * (world - 1) if args.index_pattern == "remote" else per, (n,), device="cuda", dtype=torch.int64, generator=gen)
+            if args.index_pattern == "remote":
+                r = r + (r >= rank * per).to(torch.int64) * per  # skip my own partition
+            else:
+                r = r + rank * per
+            idx_dev.append(r)
     if args.index_pattern == "sequential":  # diagnostic only: contiguous rows = the kernel's ceiling without DRAM page misses
         idx_dev = [(torch.arange(n, device="cuda", dtype=torch.int64) + (b * n * 7) % max(1, rows_total - n)) for b in range(n_batches)]
     out = torch.empty(n, dim, device="cuda", dtype=th_dtype)

@@ -1,0 +1,28 @@
+echo "### correctness with the bulk path"
+WG_BULK=1 python -m pytest tests/test_gather_scatter_gpu.py tests/test_ref_parity_gpu.py -m gpu -q -x 2>&1 | tail -3
+T1="python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline"
+T2="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e"
+run() { echo "== $*"; env "${@:2}" $1 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print('   aggregate %.1f GB/s  ms %.4f  per-GPU %.1f GB/s' % (d['value'], d['ms_per_step'], d['value']/d['n_gpus']))
+    elif 'rror' in l: print('   '+l[:300])
+"; }
+run "$T1" WG_BULK=0
+run "$T1" WG_BULK=1
+run "$T1" WG_BULK=1 WG_BULK_SLOT_KB=4
+run "$T1" WG_BULK=1 WG_BULK_SLOT_KB=2
+run "$T1" WG_BULK=1 WG_BULK_SLOT_KB=12
+run "$T1 --dim 128 --dtype fp16 --rows-per-gpu 125000000" WG_BULK=1
+run "$T1 --dim 128 --dtype fp16 --rows-per-gpu 125000000" WG_BULK=1 WG_BULK_SLOT_KB=4
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+run "$T2 --index-pattern remote" WG_BULK=0 WG_CACHE_POLICY=2
+run "$T2 --index-pattern remote" WG_BULK=1
+run "$T2 --index-pattern remote" WG_BULK=1 WG_BULK_SLOT_KB=4
+run "$T2 --index-pattern remote" WG_BULK=1 WG_BULK_SLOT_KB=12
+run "$T2 --index-pattern random" WG_BULK=1
+run "$T2 --index-pattern random" WG_BULK=0 WG_CACHE_POLICY=2
+run "$T2 --index-pattern random --dim 128 --dtype fp16 --rows-per-gpu 125000000" WG_BULK=1
+fi

@@ -4,6 +4,7 @@
  * (cpp/src/wholememory_ops/functions/gather_scatter_func.cuh:378-517, :600-661) and its
  * dtype-pair registry (register.hpp): same accepted dtype pairs plus bf16.
  */
+#include "gather_bulk.cuh"
 #include "gather_scatter.cuh"
 #include "ops_internal.hpp"
 
@@ -110,6 +111,36 @@ void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_r
   *grid          = (int)std::max<int64_t>(1, std::min(max_grid, need));
 }
 
+/* TMA-bulk variant (gather_bulk.cuh).  Returns false when the shape does not qualify. */
+template <typename IdxT, bool GATHER>
+bool launch_bulk(const table_ref& t, row_geom g, const void* idx, int64_t n, char* dense, int64_t row_bytes, int sms, cudaStream_t s)
+{
+  static const int slot_kb = env_int("WG_BULK_SLOT_KB", 8);
+  int R = 32;
+  while (R > 1 && (int64_t)R * row_bytes > (int64_t)slot_kb * 1024) R >>= 1;
+  size_t smem = 128 + (size_t)kBulkWarps * kBulkStages * R * row_bytes;
+  if (smem > 220 * 1024) return false;
+  auto kernel = row_move_bulk_kernel<IdxT, GATHER>;
+  static bool attr_set = false; /* per instantiation */
+  if (!attr_set) {
+    WM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBulkWarps * 32, smem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
+  int total_sms = sm_count();
+  if (sms <= 0 || sms > total_sms) sms = total_sms;
+  g.batch_rows   = R;
+  int64_t nbatch = (n + R - 1) / R;
+  int64_t need   = (nbatch + kBulkWarps - 1) / kBulkWarps;
+  int grid       = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * occ, need));
+  kernel<<<grid, kBulkWarps * 32, smem, s>>>(t, g, static_cast<const IdxT*>(idx), n, dense, (int)row_bytes);
+  return true;
+}
+
 }  // namespace
 
 table_ref make_flat_table_ref(void* base)
@@ -159,8 +190,10 @@ void row_move(bool gather,
   g.table_offset_bytes = td.storage_offset * et;
   g.table_stride_bytes = td.stride * et;
   g.dense_stride_bytes = dd.stride * ed;
-  static const int cache_policy = env_int("WG_CACHE_POLICY", 0);
-  g.policy                      = cache_policy;
+  /* LDG kernel: local rows stream past L1 (no_allocate); possibly-remote rows use plain L1-allocating loads,
+   * which measured 4.5 % faster over NVLink (657 vs 629 GB/s). WG_CACHE_POLICY overrides. */
+  static const int cache_policy = env_int("WG_CACHE_POLICY", -1);
+  g.policy                      = cache_policy >= 0 ? cache_policy : (tref.has_remote ? 2 : 0);
 
   /* alignment shared by both sides, in bytes of each side's element */
   uint64_t t_bits = (uint64_t)g.table_offset_bytes | (uint64_t)g.table_stride_bytes;
@@ -173,6 +206,23 @@ void row_move(bool gather,
     g.row_elems             = (int)td.sizes[1];
     set_units(&g, row_bytes / vec);
     int grid                = 1;
+    /* Kernel choice, measured on B200 (profiles/README.md):
+     *  - rows that can be remote (peer HBM over NVLink, host memory): copy-engine kernel (cp.async.bulk) --
+     *    2 GPUs, uniform indices, 1 KiB rows: 0.829 ms vs 0.895 ms for the LDG kernel (NVLink ceiling 0.817 ms);
+     *  - all rows in local HBM: LDG/STG kernel (0.369 ms vs 0.377-0.390 ms for the bulk kernel).
+     * WG_BULK=0/1 forces one or the other. */
+    static const int bulk_mode = env_int("WG_BULK", -1);
+    const bool use_bulk        = bulk_mode >= 0 ? bulk_mode != 0 : tref.has_remote != 0;
+    if (use_bulk && vec == 16 && row_bytes >= 64) {
+      bool done = gather ? (idx64 ? launch_bulk<int64_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream)
+                                  : launch_bulk<int32_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream))
+                         : (idx64 ? launch_bulk<int64_t, false>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream)
+                                  : launch_bulk<int32_t, false>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream));
+      if (done) {
+        WM_CUDA(cudaGetLastError());
+        return;
+      }
+    }
     plan(n, row_bytes, sms, vec_blocks_per_sm(), &g.batch_rows, &grid);
     if (gather) {
       if (idx64) launch_vec_w<int64_t, true>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);

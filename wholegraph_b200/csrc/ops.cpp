@@ -32,10 +32,16 @@ table_ref make_table_ref(wholememory_tensor_t t)
   }
   wholememory_handle_t h = t->handle;
   WM_EXPECT(h->peer_mapped, WHOLEMEMORY_LOGIC_ERROR, "WholeMemory handle is not addressable from this rank");
-  if (h->flat_base != nullptr) return make_flat_table_ref(h->flat_base);
-  const int ws = h->comm->world_size;
+  const int ws         = h->comm->world_size;
+  const int has_remote = (ws > 1 || h->location == WHOLEMEMORY_ML_HOST) ? 1 : 0;
+  if (h->flat_base != nullptr) {
+    table_ref f  = make_flat_table_ref(h->flat_base);
+    f.has_remote = has_remote;
+    return f;
+  }
   table_ref r{};
   r.nranks      = ws;
+  r.has_remote  = has_remote;
   r.chunk_bytes = h->chunk_stride;
   if (ws <= kMaxInlineRanks) {
     r.mode = h->regular ? table_ref::CHUNK_REGULAR : table_ref::CHUNK_IRREGULAR;

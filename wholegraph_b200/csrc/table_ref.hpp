@@ -11,6 +11,7 @@ struct table_ref {
   enum : int { FLAT = 0, CHUNK_REGULAR = 1, CHUNK_IRREGULAR = 2, DEVTAB_REGULAR = 3, DEVTAB_IRREGULAR = 4 };
   int mode;
   int nranks;
+  int has_remote; /* some rows live outside this GPU's HBM (peer GPUs over NVLink, or host memory) */
   uint64_t chunk_bytes;                        /* *_REGULAR: bytes owned by each rank */
   char* base[kMaxInlineRanks];                 /* FLAT: base[0]; CHUNK_*: start of rank r's partition */
   uint64_t first_byte[kMaxInlineRanks + 1];    /* CHUNK_IRREGULAR: partition start offsets */
