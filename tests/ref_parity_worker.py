@@ -29,6 +29,10 @@ CASES = [
     ("chunked", "cpu", O.DT_HALF, O.DT_FLOAT, 300, 304, np.int32, 1200),
 ]
 ROWS = 6007
+if os.environ.get("WG_GOLDEN_SMALL"):  # tools/make_golden.sh: a compact version of the same cases, small enough to commit
+    ROWS = 307
+    CASES = [(mt, loc, a, b, min(cols, 40), min(stride, 40) if stride != cols else min(cols, 40), idt, min(n, 150))
+             for (mt, loc, a, b, cols, stride, idt, n) in CASES]
 
 
 def case_inputs(ci):

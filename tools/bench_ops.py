@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Device-timed micro-benchmarks of the other hot-path kernels (scatter, fused LazyAdam step, neighbor sampling) with
+their roofline arithmetic.  One GPU, world_size 1.  Not the headline metric (that is bench.py)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import wholegraph_b200.binding as wmb  # noqa: E402
+import wholegraph_b200.torch as wgth  # noqa: E402
+from wholegraph_b200.torch.wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor  # noqa: E402
+
+HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, steps=20, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="scatter,adam,sample")
+    ap.add_argument("--rows", type=int, default=20_000_000)
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
+    comm = wgth.WholeMemoryCommunicator(wmb.create_communicator(wmb.create_unique_id(), 0, 1))
+    env = get_wholegraph_env_fns()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    out = []
+    if "scatter" in args.what:
+        rows, dim, n = args.rows, 256, 1 << 20
+        t = wgth.create_wholememory_tensor(comm, "continuous", "cuda", [rows, dim], torch.float32, [dim, 1])
+        src = torch.randn(n, dim, device="cuda")
+        idxs = [torch.randperm(rows, device="cuda", generator=g)[:n].contiguous() for _ in range(4)]
+        w_src = wrap_torch_tensor(src)
+        w_idx = [wrap_torch_tensor(i) for i in idxs]
+        k = [0]
+
+        def f():
+            wmb.wholememory_scatter_op(w_src, w_idx[k[0] % 4], t.wmb_tensor, env, get_stream())
+            k[0] += 1
+        ms = timeit(f)
+        alg = n * (dim * 4 * 2 + 8)
+        out.append({"op": "scatter fp32 %dx%d, %d rows" % (rows, dim, n), "ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
+        wgth.destroy_wholememory_tensor(t)
+    if "adam" in args.what:
+        rows, dim, n = args.rows // 4, 512, 1 << 18
+        emb = wgth.create_embedding(comm, "distributed", "cuda", torch.float32, [rows, dim])
+        opt = wgth.create_wholememory_optimizer(emb, "adam", {}, global_comm=comm)
+        grads = torch.randn(n, dim, device="cuda")
+        for name, idx in (("uniform", torch.randint(0, rows, (n,), device="cuda", generator=g)),
+                          ("unique", torch.randperm(rows, device="cuda", generator=g)[:n].contiguous())):
+            w_i, w_g = wrap_torch_tensor(idx), wrap_torch_tensor(grads)
+            uniq = int(torch.unique(idx).numel())
+
+            def f():
+                wmb.EmbeddingGatherGradientApply(emb.wmb_embedding, w_i, w_g, False, 0.01, env, get_stream())
+            ms = timeit(f, steps=10, warmup=3)
+            alg = n * dim * 4 + uniq * (6 * dim * 4 + 16) + n * 8
+            out.append({"op": "fused dedup+LazyAdam %dx%d, %d grads (%s, %d unique), whole call incl. sort" % (rows, dim, n, name, uniq),
+                        "ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
+        wgth.destroy_wholememory_optimizer(opt)
+        wgth.destroy_embedding(emb)
+    if "sample" in args.what:
+        nodes = 10_000_000
+        deg = torch.clamp((torch.rand(nodes, device="cuda", generator=g) ** -0.7).long(), max=10000)
+        row_ptr = torch.zeros(nodes + 1, dtype=torch.int64, device="cuda")
+        row_ptr[1:] = torch.cumsum(deg, 0)
+        edges = int(row_ptr[-1].item())
+        rp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [nodes + 1], torch.int64, [1])
+        cp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [edges], torch.int32, [1])
+        rp.get_local_tensor()[0].copy_(row_ptr)
+        cp.get_local_tensor()[0].copy_(torch.randint(0, nodes, (edges,), device="cuda", dtype=torch.int32, generator=g))
+        for ncenter, k in ((1024, 25), (25 * 1024, 10), (262144, 25), (262144, 10)):
+            centers = torch.randint(0, nodes, (ncenter,), device="cuda", generator=g)
+
+            def f():
+                return wgth.unweighted_sample_without_replacement(rp.wmb_tensor, cp.wmb_tensor, centers, k, random_seed=7)
+            ms = timeit(f, steps=10, warmup=3)
+            total = int(f()[0][-1].item())
+            out.append({"op": "unweighted sample %d centers k=%d on %d-node/%d-edge CSR (whole call: count+scan+sync+sample)" % (ncenter, k, nodes, edges),
+                        "ms": round(ms, 4), "Msamples_per_s": round(total / ms / 1e3, 2), "samples": total})
+        wgth.destroy_wholememory_tensor(rp)
+        wgth.destroy_wholememory_tensor(cp)
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()

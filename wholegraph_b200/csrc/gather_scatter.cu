@@ -115,7 +115,7 @@ void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_r
 template <typename IdxT, bool GATHER>
 bool launch_bulk(const table_ref& t, row_geom g, const void* idx, int64_t n, char* dense, int64_t row_bytes, int sms, cudaStream_t s)
 {
-  static const int slot_kb = env_int("WG_BULK_SLOT_KB", 8);
+  static const int slot_kb = env_int("WG_BULK_SLOT_KB", 4); /* 4 KiB slots: 754 vs 744 GB/s per GPU at 8 GPUs, 0.377 vs 0.390 ms local */
   int R = 32;
   while (R > 1 && (int64_t)R * row_bytes > (int64_t)slot_kb * 1024) R >>= 1;
   size_t smem = 128 + (size_t)kBulkWarps * kBulkStages * R * row_bytes;
