@@ -655,6 +655,20 @@ def csr_unweighted_sample_without_replacement(wm_csr_row_ptr_tensor, wm_csr_col_
         _env_ptr(p_env_fns_int), c_void_p(stream_int)))
 
 
+def append_unique(target_node_tensor, neighbor_node_tensor, output_unique_node_memory_handle,
+                  output_neighbor_raw_to_unique_mapping_tensor, p_env_fns_int, stream_int):
+    _chk(lib.graph_append_unique(c_void_p(target_node_tensor.get_c_handle()), c_void_p(neighbor_node_tensor.get_c_handle()),
+                                 c_void_p(output_unique_node_memory_handle),
+                                 c_void_p(output_neighbor_raw_to_unique_mapping_tensor.get_c_handle()),
+                                 _env_ptr(p_env_fns_int), c_void_p(stream_int)))
+
+
+def add_csr_self_loop(csr_row_ptr_tensor, csr_col_ptr_tensor, csr_row_ptr_self_tensor, csr_col_ptr_self_tensor, stream_int):
+    _chk(lib.csr_add_self_loop(c_void_p(csr_row_ptr_tensor.get_c_handle()), c_void_p(csr_col_ptr_tensor.get_c_handle()),
+                               c_void_p(csr_row_ptr_self_tensor.get_c_handle()), c_void_p(csr_col_ptr_self_tensor.get_c_handle()),
+                               c_void_p(stream_int)))
+
+
 def host_generate_random_positive_int(random_seed, sub_sequence, output):
     _chk(lib.generate_random_positive_int_cpu(random_seed, sub_sequence, c_void_p(output.get_c_handle())))
 

@@ -185,7 +185,7 @@ wholememory_error_code_t gradient_apply(wholememory_embedding_t e,
   if (comm->world_size == 1) {
     /* nothing to exchange: merge + update straight from the caller's buffers */
     merge_and_update_rows(e->optimizer->type, idx_ptr, idesc->dtype, n, grad_ptr, gdesc->strides[0], rows, e->optimizer->params, lr,
-                          total_rows, env, stream);
+                          total_rows, /*may_have_negative=*/true, env, stream);
     return WHOLEMEMORY_SUCCESS;
   }
 
@@ -206,7 +206,9 @@ wholememory_error_code_t gradient_apply(wholememory_embedding_t e,
   }
   exchange_rows(plan, comm, out_p, in_p, (size_t)D * sizeof(float), /*to_owner=*/true, stream);
   merge_and_update_rows(e->optimizer->type, plan.recv_idx.ptr(), idesc->dtype, plan.n_recv, in_p, D, rows, e->optimizer->params, lr,
-                        total_rows, env, stream);
+                        total_rows, /*may_have_negative=*/false, env, stream);
+  /* exchange buffers are released on return */
+  WM_CUDA(cudaStreamSynchronize(stream));
   return WHOLEMEMORY_SUCCESS;
 }
 

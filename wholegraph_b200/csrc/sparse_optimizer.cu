@@ -71,9 +71,14 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
                                                                 optimizer_params p,
                                                                 float lr)
 {
-  const int b       = blockIdx.x;
-  const IdxT row_id = sorted_idx[b];
-  if (b > 0 && sorted_idx[b - 1] == row_id) return; /* not the head of its run */
+  const int b = blockIdx.x;
+  /* four independent loads up front (one DRAM round trip): my id, my neighbours' ids, my gradient position */
+  const IdxT row_id  = sorted_idx[b];
+  const IdxT prev_id = b > 0 ? sorted_idx[b - 1] : row_id;
+  const IdxT next_id = b + 1 < n ? sorted_idx[b + 1] : row_id;
+  const int pos0     = sorted_pos[b];
+  if (b > 0 && prev_id == row_id) return; /* not the head of its run */
+  const bool has_dups = b + 1 < n && next_id == row_id;
   const int64_t local = (int64_t)row_id - rows.local_row_start;
   if (local < 0 || local >= rows.local_rows) return; /* negative / foreign ids are ignored */
 
@@ -89,15 +94,22 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
   }
 
   for (int c = threadIdx.x * VEC; c < rows.dim; c += blockDim.x * VEC) {
+    /* issue the row's W / state loads first: they do not depend on the gradient chain, so all of the
+     * CTA's DRAM reads are in flight together (measured: this kernel is latency-bound per CTA) */
+    fvec<VEC> wv = ldv<VEC>(w + c);
+    fvec<VEC> sv0, sv1;
+    if (OPT != WHOLEMEMORY_OPT_SGD) sv0 = ldv<VEC>(s0 + c);
+    if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) sv1 = ldv<VEC>(s1 + c);
     /* 1. merge duplicates: g = g[pos0] + g[pos1] + ... in arrival order */
-    fvec<VEC> g = ldv<VEC>(grads + (int64_t)sorted_pos[b] * grad_stride + c);
-    for (int j = b + 1; j < n && sorted_idx[j] == row_id; ++j) {
-      fvec<VEC> o = ldv<VEC>(grads + (int64_t)sorted_pos[j] * grad_stride + c);
+    fvec<VEC> g = ldv<VEC>(grads + (int64_t)pos0 * grad_stride + c);
+    if (has_dups) {
+      for (int j = b + 1; j < n && sorted_idx[j] == row_id; ++j) {
+        fvec<VEC> o = ldv<VEC>(grads + (int64_t)sorted_pos[j] * grad_stride + c);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) g.at(k) += o.at(k);
+        for (int k = 0; k < VEC; ++k) g.at(k) += o.at(k);
+      }
     }
     /* 2. optimizer */
-    fvec<VEC> wv = ldv<VEC>(w + c);
     if (OPT == WHOLEMEMORY_OPT_SGD) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
@@ -108,8 +120,8 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
         wv.at(k) = embedding_value;
       }
     } else if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) {
-      fvec<VEC> mv = ldv<VEC>(s0 + c);
-      fvec<VEC> vv = ldv<VEC>(s1 + c);
+      fvec<VEC>& mv = sv0;
+      fvec<VEC>& vv = sv1;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         float grad_value      = g.at(k);
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
       stv<VEC>(s0 + c, mv);
       stv<VEC>(s1 + c, vv);
     } else if (OPT == WHOLEMEMORY_OPT_ADAGRAD) {
-      fvec<VEC> sv = ldv<VEC>(s0 + c);
+      fvec<VEC>& sv = sv0;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         float grad_value      = g.at(k);
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
       }
       stv<VEC>(s0 + c, sv);
     } else { /* RMSPROP */
-      fvec<VEC> vv = ldv<VEC>(s0 + c);
+      fvec<VEC>& vv = sv0;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         float grad_value      = g.at(k);
@@ -192,7 +204,8 @@ void launch_fused(int opt, const IdxT* si, const int* sp, int n, const float* g,
 
 template <typename IdxT>
 void merge_update_typed(int opt, const void* idx, int64_t n, const float* grads, int64_t grad_stride, const optimizer_rows& rows,
-                        const optimizer_params& p, float lr, int64_t total_rows, wholememory_env_func_t* env, cudaStream_t s)
+                        const optimizer_params& p, float lr, int64_t total_rows, bool may_have_negative, wholememory_env_func_t* env,
+                        cudaStream_t s)
 {
   const wholememory_dtype_t idt = sizeof(IdxT) == 8 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
   temp_buffer sorted_idx_b(env), pos_in_b(env), pos_out_b(env), cub_b(env);
@@ -201,8 +214,13 @@ void merge_update_typed(int opt, const void* idx, int64_t n, const float* grads,
   auto* pos_out    = static_cast<int*>(pos_out_b.device((size_t)n, WHOLEMEMORY_DT_INT));
   iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pos_in, (int)n);
   /* ids are < total_rows (negatives keep their sign bit and sort first): only sort the bits in use */
+  /* non-negative ids below total_rows only need ceil(log2(total_rows)) bits: 3 onesweep passes instead of 8 for 5M rows.
+   * Negative ids (ignored by the kernel) would alias into that range, so they force the full width. */
   int end_bit = (int)sizeof(IdxT) * 8;
-  (void)total_rows;
+  if (total_rows > 0 && !may_have_negative) {
+    end_bit = 1;
+    while (end_bit < (int)sizeof(IdxT) * 8 && ((int64_t)1 << end_bit) < total_rows) ++end_bit;
+  }
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const IdxT*>(idx), sorted_idx, pos_in, pos_out, (int)n, 0, end_bit, s);
   void* cub_tmp = cub_b.device(cub_bytes, WHOLEMEMORY_DT_INT8);
@@ -213,8 +231,8 @@ void merge_update_typed(int opt, const void* idx, int64_t n, const float* grads,
   if (vec4) launch_fused<IdxT, 4>(opt, sorted_idx, pos_out, (int)n, grads, grad_stride, rows, p, lr, s);
   else launch_fused<IdxT, 1>(opt, sorted_idx, pos_out, (int)n, grads, grad_stride, rows, p, lr, s);
   WM_CUDA(cudaGetLastError());
-  /* temporaries go back to the caller's allocator when this frame unwinds */
-  WM_CUDA(cudaStreamSynchronize(s));
+  /* Temporaries go back to the caller's allocator when this frame unwinds WITHOUT a host sync, like the reference's
+   * dedup/optimizer stage: torch's caching allocator is stream-ordered, cudaFree (default env) synchronises itself. */
 }
 
 __global__ void fill_kernel(float* p, float v, int64_t n)
@@ -235,6 +253,7 @@ void merge_and_update_rows(int optimizer_type,
                            const optimizer_params& params,
                            float lr,
                            int64_t total_rows,
+                           bool may_have_negative,
                            wholememory_env_func_t* env,
                            cudaStream_t stream)
 {
@@ -242,9 +261,9 @@ void merge_and_update_rows(int optimizer_type,
   if (n == 0) return;
   WM_EXPECT(n < ((int64_t)1 << 31), WHOLEMEMORY_INVALID_VALUE, "too many gradient rows in one step (%ld)", (long)n);
   if (idx_dtype == WHOLEMEMORY_DT_INT64)
-    merge_update_typed<int64_t>(optimizer_type, indices, n, grads, grad_stride, rows, params, lr, total_rows, env, stream);
+    merge_update_typed<int64_t>(optimizer_type, indices, n, grads, grad_stride, rows, params, lr, total_rows, may_have_negative, env, stream);
   else if (idx_dtype == WHOLEMEMORY_DT_INT)
-    merge_update_typed<int32_t>(optimizer_type, indices, n, grads, grad_stride, rows, params, lr, total_rows, env, stream);
+    merge_update_typed<int32_t>(optimizer_type, indices, n, grads, grad_stride, rows, params, lr, total_rows, may_have_negative, env, stream);
   else
     WM_THROW(WHOLEMEMORY_LOGIC_ERROR, "gradient indices must be int32 or int64");
 }

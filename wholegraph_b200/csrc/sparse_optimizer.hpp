@@ -41,6 +41,7 @@ void merge_and_update_rows(int optimizer_type,
                            const optimizer_params& params,
                            float lr,
                            int64_t total_rows,
+                           bool may_have_negative, /* ids come straight from the caller (not filtered by the exchange) */
                            wholememory_env_func_t* env,
                            cudaStream_t stream);
 

@@ -1,7 +1,6 @@
 /*
  * Entry points the reference's binding links against but which are outside this build's scope
- * (cached embeddings; 8(f) "next": append_unique, add_self_loop, weighted
- * sampling).  They exist so that the cython binding / ctypes loader resolves every symbol, and
+ * (SURVEY section 8(f) "next": weighted sampling).  They exist so that the cython binding / ctypes loader resolves every symbol, and
  * they fail loudly with WHOLEMEMORY_NOT_IMPLEMENTED instead of silently doing nothing.
  */
 #include "wm_internal.hpp"
@@ -28,23 +27,6 @@ wholememory_error_code_t wholegraph_csr_weighted_sample_without_replacement(whol
 wholememory_error_code_t generate_exponential_distribution_negative_float_cpu(int64_t, int64_t, wholememory_tensor_t)
 {
   WM_ERROR("generate_exponential_distribution_negative_float_cpu belongs to weighted sampling (not built yet)");
-  return WHOLEMEMORY_NOT_IMPLEMENTED;
-}
-
-wholememory_error_code_t graph_append_unique(wholememory_tensor_t,
-                                             wholememory_tensor_t,
-                                             void*,
-                                             wholememory_tensor_t,
-                                             wholememory_env_func_t*,
-                                             void*)
-{
-  WM_ERROR("graph_append_unique is not built yet (SURVEY 8(f) rank 1)");
-  return WHOLEMEMORY_NOT_IMPLEMENTED;
-}
-
-wholememory_error_code_t csr_add_self_loop(wholememory_tensor_t, wholememory_tensor_t, wholememory_tensor_t, wholememory_tensor_t, void*)
-{
-  WM_ERROR("csr_add_self_loop is not built yet (SURVEY 8(f) rank 4)");
   return WHOLEMEMORY_NOT_IMPLEMENTED;
 }
 
