@@ -36,6 +36,12 @@ int tuned_unroll()
   return u;
 }
 
+int tuned_threads()
+{
+  static const int t = env_int("WG_THREADS", kThreads);
+  return t;
+}
+
 template <typename IdxT, int VEC, bool GATHER>
 void launch_vec(const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
 {
@@ -43,12 +49,12 @@ void launch_vec(const table_ref& t, const row_geom& g, const void* idx, int64_t 
   if constexpr (VEC == 16) {
     /* the 16-byte path is the hot one: loads-in-flight per lane is tunable */
     switch (tuned_unroll()) {
-      case 2: row_move_vec_kernel<IdxT, VEC, GATHER, 2><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense); return;
-      case 8: row_move_vec_kernel<IdxT, VEC, GATHER, 8><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense); return;
+      case 2: row_move_vec_kernel<IdxT, VEC, GATHER, 2><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense); return;
+      case 8: row_move_vec_kernel<IdxT, VEC, GATHER, 8><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense); return;
       default: break;
     }
   }
-  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, kThreads, 0, s>>>(t, g, ip, n, dense);
+  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense);
 }
 
 template <typename IdxT, bool GATHER>
@@ -106,9 +112,15 @@ void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_r
   static const int forced_rows = env_int("WG_BATCH_ROWS", 0);
   if (forced_rows > 0) R = forced_rows;
   int64_t nbatch = (n + R - 1) / R;
-  int64_t need   = (nbatch + (kThreads / 32) - 1) / (kThreads / 32);
+  const int wpc  = tuned_threads() / 32;
+  int64_t need   = (nbatch + wpc - 1) / wpc;
   *batch_rows    = R;
   *grid          = (int)std::max<int64_t>(1, std::min(max_grid, need));
+  /* Unless the caller restricts the SM budget, launch ONE BATCH PER WARP and let the hardware CTA scheduler walk the
+   * index array in order: measured 0.340 ms vs 0.372 ms for the persistent grid-stride form on C2 (0.966 vs 0.883 of
+   * HBM peak, profiles/README.md).  WG_GRID_MODE=0 restores the persistent grid (developer knob). */
+  static const int grid_mode = env_int("WG_GRID_MODE", 1);
+  if (grid_mode == 1 && sms == total_sms) *grid = (int)std::min<int64_t>(need, 0x7fffffff);
 }
 
 /* TMA-bulk variant (gather_bulk.cuh).  Returns false when the shape does not qualify. */
@@ -206,13 +218,12 @@ void row_move(bool gather,
     g.row_elems             = (int)td.sizes[1];
     set_units(&g, row_bytes / vec);
     int grid                = 1;
-    /* Kernel choice, measured on B200 (profiles/README.md):
-     *  - rows that can be remote (peer HBM over NVLink, host memory): copy-engine kernel (cp.async.bulk) --
-     *    2 GPUs, uniform indices, 1 KiB rows: 0.829 ms vs 0.895 ms for the LDG kernel (NVLink ceiling 0.817 ms);
-     *  - all rows in local HBM: LDG/STG kernel (0.369 ms vs 0.377-0.390 ms for the bulk kernel).
-     * WG_BULK=0/1 forces one or the other. */
-    static const int bulk_mode = env_int("WG_BULK", -1);
-    const bool use_bulk        = bulk_mode >= 0 ? bulk_mode != 0 : tref.has_remote != 0;
+    /* Kernel choice, measured on B200 (profiles/README.md): the LDG/STG kernel launched one-batch-per-warp wins
+     * everywhere -- local HBM 0.345 ms (bulk: 0.377-0.390), 2 GPUs uniform indices 0.820-0.825 ms (bulk: 0.829-0.845),
+     * remote-only 669 GB/s (bulk: 657-660).  The copy-engine kernel (cp.async.bulk, gather_bulk.cuh) stays available
+     * behind WG_BULK=1; it frees the SMs' LSU/register path and is the basis for a future SM-budgeted (gather_sms) mode. */
+    static const int bulk_mode = env_int("WG_BULK", 0);
+    const bool use_bulk        = bulk_mode != 0;
     if (use_bulk && vec == 16 && row_bytes >= 64) {
       bool done = gather ? (idx64 ? launch_bulk<int64_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream)
                                   : launch_bulk<int32_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream))

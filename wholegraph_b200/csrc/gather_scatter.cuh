@@ -164,7 +164,7 @@ __device__ __forceinline__ char* shfl_ptr(char* p, int src_lane)
  * lanes, UNROLL at a time (loads first, then stores).
  */
 template <typename IdxT, int VEC, bool GATHER, int UNROLL>
-__global__ void __launch_bounds__(256) row_move_vec_kernel(table_ref tref,
+__global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
                                                           row_geom g,
                                                           const IdxT* __restrict__ indices,
                                                           int64_t n,
