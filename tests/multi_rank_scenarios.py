@@ -18,6 +18,7 @@ def _setup(rank, world, port, ngpus, env):
     os.environ.update(env)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["WG_TEST_SHARED_GPU"] = "1" if ngpus < world else "0"
     import torch
     import wholegraph_b200.torch as wgth
     torch.cuda.set_device(rank % ngpus)
@@ -184,7 +185,76 @@ def scenario_sampling(rank, world, comm):
             wmb.destroy_wholememory_tensor(cp)
 
 
-SCENARIOS = {"gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+def scenario_file_io(rank, world, comm):
+    """Round trip through the reference's on-disk format (raw row-major part files "<prefix>_part_i_of_n"):
+    store per-rank parts, reload them into differently typed / partitioned tables, and reload files whose part
+    count differs from the world size."""
+    import tempfile
+    import torch
+    import wholegraph_b200.torch as wgth
+    from oracle import oracle as O
+    rows, cols, stride = 3001, 13, 16
+    rng = np.random.default_rng(77)
+    host = rng.standard_normal((rows, stride)).astype(np.float32)
+    base = os.path.join(tempfile.gettempdir(), "wgb200_io_%s" % os.environ["MASTER_PORT"])
+    # 1. files written by "someone else": 3 part files of the [rows, cols] matrix, loaded by `world` ranks
+    if rank == 0:
+        cuts = [0, 1000, 1001, rows]
+        for i in range(3):
+            host[cuts[i]:cuts[i + 1], :cols].copy().tofile("%s_src_part_%d_of_3" % (base, i))
+    comm.barrier()
+    filelist = ["%s_src_part_%d_of_3" % (base, i) for i in range(3)]
+    for mt, loc in (("chunked", "cuda"), ("distributed", "cuda"), ("continuous", "cpu")):
+        t = wgth.create_wholememory_tensor(comm, mt, loc, [rows, cols], torch.float32, [stride, 1])
+        t.from_filelist(filelist)
+        local, first = t.get_local_tensor(host_view=(loc == "cpu"))
+        assert np.array_equal(local.cpu().numpy(), host[first:first + local.shape[0], :cols]), (mt, loc)
+        idx = torch.from_numpy(rng.integers(0, rows, size=500).astype(np.int64)).cuda()
+        assert np.array_equal(t.gather(idx).cpu().numpy(), host[idx.cpu().numpy(), :cols])
+        # 2. store my part, then reload everything into a table of another type
+        t.to_file_prefix(base + "_dump_" + mt)
+        comm.barrier()
+        t2 = wgth.create_wholememory_tensor_from_filelist(comm, "continuous", "cuda",
+                                                          ["%s_dump_%s_part_%d_of_%d" % (base, mt, r, world) for r in range(world)],
+                                                          torch.float32, last_dim_size=cols)
+        assert t2.shape == (rows, cols)
+        l2, f2 = t2.get_local_tensor()
+        assert np.array_equal(l2.cpu().numpy(), host[f2:f2 + l2.shape[0], :cols])
+        comm.barrier()
+        wgth.destroy_wholememory_tensor(t2)
+        wgth.destroy_wholememory_tensor(t)
+    # 3. embedding + optimizer state checkpoint round trip
+    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [rows, cols])
+    opt = wgth.create_wholememory_optimizer(emb, "adam", {}, global_comm=comm)
+    lw, fw = emb.get_embedding_tensor().get_local_tensor()
+    lw.copy_(torch.from_numpy(host[fw:fw + lw.shape[0], :cols]))
+    comm.barrier()
+    gi = torch.from_numpy(np.random.default_rng(5 + rank).integers(0, rows, size=400).astype(np.int64)).cuda()
+    if os.environ.get("WG_TEST_SHARED_GPU") != "1":  # the gradient exchange needs NCCL = one GPU per rank
+        emb.add_gradients(gi, torch.ones(400, cols, device="cuda"))
+        emb.need_apply = True
+        opt.step(0.1)
+    emb.save(base + "_ckpt")
+    comm.barrier()
+    emb2 = wgth.create_embedding(comm, "distributed", "cuda", torch.float32, [rows, cols])
+    opt2 = wgth.create_wholememory_optimizer(emb2, "adam", {}, global_comm=comm)
+    emb2.load(base + "_ckpt")
+    for get in (lambda e: e.get_embedding_tensor(), lambda e: e.get_optimizer_state("m"), lambda e: e.get_optimizer_state("v"),
+                lambda e: e.get_optimizer_state("beta12t")):
+        a, _ = get(emb).get_local_tensor()
+        b, _ = get(emb2).get_local_tensor()
+        assert torch.equal(a, b)
+    comm.barrier()
+    for o, e in ((opt, emb), (opt2, emb2)):
+        wgth.destroy_wholememory_optimizer(o)
+        wgth.destroy_embedding(e)
+    if rank == 0:
+        import glob
+        for f in glob.glob(base + "_*"):
+            os.remove(f)
+
+
+SCENARIOS = {"file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):

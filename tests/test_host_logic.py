@@ -182,9 +182,13 @@ def test_optimizer_parameter_names(wmb):
 
 def test_out_of_scope_entry_points_say_so(wmb):
     L = _lib.lib
-    assert L.wholememory_load_from_file(None, 0, 0, 0, None, 0, 0) == wmb.WholeMemoryErrorCode.NotImplemented
-    assert L.graph_append_unique(None, None, None, None, None, None) == wmb.WholeMemoryErrorCode.NotImplemented
-    assert L.csr_add_self_loop(None, None, None, None, None) == wmb.WholeMemoryErrorCode.NotImplemented
+    assert L.wholegraph_csr_weighted_sample_without_replacement(None, None, None, None, 5, None, None, None, None, 0, None,
+                                                                None) == wmb.WholeMemoryErrorCode.NotImplemented
+    assert L.generate_exponential_distribution_negative_float_cpu(0, 0, None) == wmb.WholeMemoryErrorCode.NotImplemented
+    # built ops diagnose null arguments instead of crashing
+    assert L.wholememory_load_from_file(None, 0, 0, 0, None, 0, 0) == wmb.WholeMemoryErrorCode.InvalidInput
+    assert L.graph_append_unique(None, None, None, None, None, None) == wmb.WholeMemoryErrorCode.InvalidInput
+    assert L.csr_add_self_loop(None, None, None, None, None) == wmb.WholeMemoryErrorCode.InvalidInput
     with pytest.raises(ValueError):
         wmb.create_cache_policy(wmb.PyWholeMemoryComm(None), wmb.MtChunked, wmb.MlDevice, wmb.AtReadOnly, 2.0)
 

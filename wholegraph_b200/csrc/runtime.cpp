@@ -201,22 +201,4 @@ int fork_get_device_count()
 
 bool wholememory_is_build_with_nvshmem() { return false; }
 
-wholememory_error_code_t wholememory_load_from_file(wholememory_handle_t,
-                                                    size_t,
-                                                    size_t,
-                                                    size_t,
-                                                    const char**,
-                                                    int,
-                                                    int)
-{
-  WM_ERROR("wholememory_load_from_file: file I/O is outside this build's scope (SURVEY 8(f) rank 3)");
-  return WHOLEMEMORY_NOT_IMPLEMENTED;
-}
-
-wholememory_error_code_t wholememory_store_to_file(wholememory_handle_t, size_t, size_t, size_t, const char*)
-{
-  WM_ERROR("wholememory_store_to_file: file I/O is outside this build's scope (SURVEY 8(f) rank 3)");
-  return WHOLEMEMORY_NOT_IMPLEMENTED;
-}
-
 } /* extern "C" */

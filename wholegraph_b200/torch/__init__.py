@@ -3,7 +3,8 @@ from .comm import (WholeMemoryCommunicator, create_group_communicator, destroy_c
                    get_global_communicator, get_local_device_communicator, get_local_node_communicator,
                    set_world_info, split_communicator)
 from .initialize import finalize, init, init_torch_env, init_torch_env_and_create_wm_comm
-from .tensor import WholeMemoryTensor, create_wholememory_tensor, destroy_wholememory_tensor
+from .tensor import (WholeMemoryTensor, create_wholememory_tensor, create_wholememory_tensor_from_filelist,
+                     destroy_wholememory_tensor)
 from .embedding import (WholeMemoryEmbedding, WholeMemoryEmbeddingModule, WholeMemoryOptimizer,  # noqa: E402
                         create_embedding, create_wholememory_cache_policy, create_wholememory_optimizer,
                         destroy_embedding, destroy_wholememory_cache_policy, destroy_wholememory_optimizer)

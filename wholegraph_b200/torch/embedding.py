@@ -159,6 +159,19 @@ class WholeMemoryEmbedding(object):
         return self.optimizer_states[state_name]
 
 
+    def save(self, file_prefix: str):
+        """Checkpoint the embedding rows and every optimizer state (one part file per rank and tensor)."""
+        self.get_embedding_tensor().to_file_prefix(file_prefix + "_embedding_tensor")
+        for state_name in self.get_optimizer_state_names():
+            self.get_optimizer_state(state_name).to_file_prefix(file_prefix + "_" + state_name)
+
+    def load(self, file_prefix: str, *, ignore_embedding: bool = False, part_count: Union[int, None] = None):
+        if ignore_embedding is False:
+            self.get_embedding_tensor().from_file_prefix(file_prefix + "_embedding_tensor", part_count)
+        for state_name in self.get_optimizer_state_names():
+            self.get_optimizer_state(state_name).from_file_prefix(file_prefix + "_" + state_name, part_count)
+
+
 def create_embedding(comm: WholeMemoryCommunicator, memory_type: str, memory_location: str, dtype: torch.dtype,
                      sizes: List[int], *, cache_policy: Union[WholeMemoryCachePolicy, None] = None,
                      embedding_entry_partition: Union[List[int], None] = None, random_init: bool = False,

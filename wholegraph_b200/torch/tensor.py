@@ -5,8 +5,8 @@ import torch
 
 from .. import binding as wmb
 from .comm import WholeMemoryCommunicator
-from .utils import (str_to_wmb_wholememory_location, str_to_wmb_wholememory_memory_type,
-                    torch_dtype_to_wholememory_dtype, wholememory_dtype_to_torch_dtype)
+from .utils import (get_file_size, get_part_file_list, get_part_file_name, str_to_wmb_wholememory_location,
+                    str_to_wmb_wholememory_memory_type, torch_dtype_to_wholememory_dtype, wholememory_dtype_to_torch_dtype)
 from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
 
 WholeMemoryMemoryType = wmb.WholeMemoryMemoryType
@@ -84,8 +84,19 @@ class WholeMemoryTensor(object):
             filelist = [filelist]
         self.wmb_tensor.from_filelist(filelist, round_robin_size)
 
+    def from_file_prefix(self, file_prefix: str, part_count: Union[int, None] = None):
+        """Load from files named "%s_part_%d_of_%d" % (prefix, part_id, part_count)."""
+        if part_count is None:
+            part_count = self.get_comm().get_size()
+        self.from_filelist(get_part_file_list(file_prefix, part_count))
+
     def local_to_file(self, filename: str):
+        """Store this rank's rows; all ranks call it together with different file names."""
         self.wmb_tensor.to_file(filename)
+
+    def to_file_prefix(self, file_prefix: str):
+        wm_comm = self.get_comm()
+        self.local_to_file(get_part_file_name(file_prefix, wm_comm.get_rank(), wm_comm.get_size()))
 
 
 def create_wholememory_tensor(comm: WholeMemoryCommunicator, memory_type: str, memory_location: str, sizes: List[int],
@@ -111,6 +122,33 @@ def create_wholememory_tensor(comm: WholeMemoryCommunicator, memory_type: str, m
     wm_location = str_to_wmb_wholememory_location(memory_location)
     return WholeMemoryTensor(
         wmb.create_wholememory_tensor(td, comm.wmb_comm, wm_memory_type, wm_location, tensor_entry_partition))
+
+
+def create_wholememory_tensor_from_filelist(comm: WholeMemoryCommunicator, memory_type: str, memory_location: str,
+                                            filelist: Union[List[str], str], dtype: torch.dtype, last_dim_size: int = 0,
+                                            last_dim_strides: int = -1, tensor_entry_partition: Union[List[int], None] = None):
+    """Create a WholeMemory tensor sized from, and filled with, a list of raw binary files
+    (last_dim_size 0 -> 1-D array, > 0 -> matrix with that many columns)."""
+    if isinstance(filelist, str):
+        filelist = [filelist]
+    element_size = torch.tensor([], dtype=dtype).element_size()
+    if last_dim_strides == -1:
+        last_dim_strides = last_dim_size if last_dim_size > 0 else 1
+    file_entry_size = element_size * last_dim_size if last_dim_size > 0 else element_size
+    total_file_size = 0
+    for filename in filelist:
+        file_size = get_file_size(filename)
+        if file_size % file_entry_size != 0:
+            raise ValueError("File %s size is %d not mutlple of %d" % (filename, file_size, file_entry_size))
+        total_file_size += file_size
+    total_entry_count = total_file_size // file_entry_size
+    if last_dim_size == 0:
+        sizes, strides = [total_entry_count], [1]
+    else:
+        sizes, strides = [total_entry_count, last_dim_size], [last_dim_strides, 1]
+    wm_tensor = create_wholememory_tensor(comm, memory_type, memory_location, sizes, dtype, strides, tensor_entry_partition)
+    wm_tensor.from_filelist(filelist)
+    return wm_tensor
 
 
 def destroy_wholememory_tensor(wm_tensor: WholeMemoryTensor):

@@ -76,3 +76,20 @@ def str_to_wmb_wholememory_optimizer_type(str_opt):
     if str_opt not in table:
         raise ValueError("WholeMemory optimizer type %s not supported, should be (sgd, adam, adagrad, rmsprop)" % str_opt)
     return table[str_opt]
+
+
+def get_file_size(filename: str):
+    import os
+    if not os.path.isfile(filename):
+        raise ValueError("File %s not found or not file" % (filename,))
+    if not os.access(filename, os.R_OK):
+        raise ValueError("File %s not readable" % (filename,))
+    return os.path.getsize(filename)
+
+
+def get_part_file_name(prefix: str, part_id: int, part_count: int):
+    return "%s_part_%d_of_%d" % (prefix, part_id, part_count)
+
+
+def get_part_file_list(prefix: str, part_count: int):
+    return [get_part_file_name(prefix, part_id, part_count) for part_id in range(part_count)]
