@@ -180,6 +180,22 @@ def scenario_sampling(rank, world, comm):
                 assert res[0].cpu().numpy().tolist() == eo.tolist(), f"offsets k={k}"
                 assert res[1].dtype == th_col and res[1].cpu().numpy().astype(np.int64).tolist() == ed.tolist(), f"dst k={k}"
                 assert res[2].cpu().numpy().tolist() == el.tolist() and res[3].cpu().numpy().tolist() == eg.tolist(), f"ids k={k}"
+            if mt == wmb.MtChunked and col_dtype == np.int64:
+                # two-hop loader step [25, 10] through GraphStructure (sample -> append_unique -> sample), config C5's shape
+                gs = wgth.GraphStructure()
+                gs.set_csr_graph(wgth.WholeMemoryTensor(rp), wgth.WholeMemoryTensor(cp))
+                seeds = torch.from_numpy(np.random.default_rng(99 + rank).permutation(nodes)[:64].astype(np.int64)).cuda()
+                tg, ei, rps, cis = gs.multilayer_sample_without_replacement(seeds, [25, 10], random_seed=4242)
+                assert len(tg) == 3 and torch.equal(tg[2], seeds)
+                for hop, (k, seed) in enumerate([(10, 4242 + 0), (25, 4242 + 1)]):
+                    centers_h = tg[hop + 1].cpu().numpy()
+                    eo, ed, el, _ = O.unweighted_sample(row_ptr, col.astype(np.int64), centers_h, k, seed)
+                    assert rps[hop].cpu().numpy().tolist() == eo.tolist()
+                    uniq = tg[hop].cpu().numpy()
+                    assert np.array_equal(uniq[:centers_h.size], centers_h)            # targets stay in front
+                    assert np.array_equal(uniq[cis[hop].cpu().numpy()], ed)            # sampled dst ids, via the unique map
+                    assert np.array_equal(ei[hop][1].cpu().numpy(), el)                # source local ids
+                    assert len(set(uniq.tolist())) == uniq.size
             comm.barrier()
             wmb.destroy_wholememory_tensor(rp)
             wmb.destroy_wholememory_tensor(cp)

@@ -47,9 +47,10 @@ def test_single_rank(scenario):
 
 
 @pytest.mark.timeout(900)
-def test_single_rank_forced_bucket_exchange():
+@pytest.mark.parametrize("scenario", ["gather_scatter", "sampling"])
+def test_single_rank_forced_bucket_exchange(scenario):
     """DISTRIBUTED ops through the partition + exchange path (self-exchange on one rank)."""
-    _run(1, "gather_scatter", env={"WG_FORCE_EXCHANGE": "1"})
+    _run(1, scenario, env={"WG_FORCE_EXCHANGE": "1"})
 
 
 @pytest.mark.timeout(900)
@@ -69,8 +70,9 @@ def test_one_rank_per_gpu(world, scenario):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("world", [2, 4])
-def test_one_rank_per_gpu_forced_nccl_exchange(world):
-    _run(world, "gather_scatter", env={"WG_FORCE_EXCHANGE": "1"})
+@pytest.mark.parametrize("scenario", ["gather_scatter", "sampling"])
+def test_one_rank_per_gpu_forced_nccl_exchange(world, scenario):
+    _run(world, scenario, env={"WG_FORCE_EXCHANGE": "1"})
 
 
 @pytest.mark.timeout(900)

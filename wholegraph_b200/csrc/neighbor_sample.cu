@@ -26,7 +26,20 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <functional>
+
 namespace wm {
+
+/* exchange.cu */
+void gather_by_exchange(wholememory_handle_t h,
+                        const wholememory_matrix_description_t& table_desc,
+                        const void* indices,
+                        const wholememory_array_description_t& idx_desc,
+                        void* output,
+                        const wholememory_matrix_description_t& out_desc,
+                        wholememory_env_func_t* env,
+                        cudaStream_t stream,
+                        int sms);
 
 namespace {
 
@@ -62,11 +75,25 @@ struct csr_ref {
   table_ref col;     /* int32|int64 elements */
   int64_t row_ptr_offset_bytes;
   int64_t col_offset_bytes;
+  /* exchange mode (DISTRIBUTED memory that is not peer-addressable): row_ptr[center] / row_ptr[center+1] were fetched
+   * up front into pre_bounds[0..n) / pre_bounds[n..2n), and col_idx is fetched afterwards from the emitted edge ids */
+  const int64_t* pre_bounds;
+  int have_col;
 };
 
 __device__ __forceinline__ int64_t load_row_ptr(const csr_ref& g, int64_t node)
 {
   return *reinterpret_cast<const int64_t*>(resolve_table_byte(g.row_ptr, (uint64_t)(g.row_ptr_offset_bytes + node * 8)));
+}
+__device__ __forceinline__ void node_bounds(const csr_ref& g, int c, int n, int64_t node, int64_t* start, int64_t* end)
+{
+  if (g.pre_bounds != nullptr) {
+    *start = g.pre_bounds[c];
+    *end   = g.pre_bounds[n + c];
+  } else {
+    *start = load_row_ptr(g, node);
+    *end   = load_row_ptr(g, node + 1);
+  }
 }
 template <typename ColT>
 __device__ __forceinline__ ColT load_col(const csr_ref& g, int64_t edge)
@@ -81,8 +108,9 @@ __global__ void sample_count_kernel(csr_ref g, const IdT* __restrict__ centers, 
   if (i > n) return;
   int c = 0;
   if (i < n) {
-    int64_t node = (int64_t)centers[i];
-    int deg      = (int)(load_row_ptr(g, node + 1) - load_row_ptr(g, node));
+    int64_t node = (int64_t)centers[i], b = 0, e = 0;
+    node_bounds(g, i, n, node, &b, &e);
+    int deg = (int)(e - b);
     c            = k > 0 ? min(deg, k) : deg;
     if (c < 0) c = 0;
   }
@@ -114,6 +142,17 @@ __host__ __device__ inline void reference_shape(int k, int* block_dim, int* item
 
 constexpr int kWarpsPerCta = 4;
 
+/* exchange mode: ids[0..n) = centers, ids[n..2n) = centers + 1 (the two row_ptr entries every center needs) */
+template <typename IdT>
+__global__ void bounds_index_kernel(const IdT* __restrict__ centers, int n, int64_t* __restrict__ ids)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t c  = (int64_t)centers[i];
+  ids[i]     = c;
+  ids[n + i] = c + 1;
+}
+
 template <typename IdT, typename ColT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(csr_ref g,
                                                                   const IdT* __restrict__ centers,
@@ -131,15 +170,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(csr_ref g,
   const int wid  = threadIdx.x >> 5;
   const int c    = blockIdx.x * kWarpsPerCta + wid;
   if (c >= n) return;
-  const int64_t node  = (int64_t)centers[c];
-  const int64_t start = load_row_ptr(g, node);
-  const int N         = (int)(load_row_ptr(g, node + 1) - start);
+  const int64_t node = (int64_t)centers[c];
+  int64_t start = 0, row_end = 0;
+  node_bounds(g, c, n, node, &start, &row_end);
+  const int N = (int)(row_end - start);
   if (N <= 0) return;
   const int off = offsets[c];
 
   if (k <= 0 || N <= k) { /* take every neighbour, CSR order */
     for (int s = lane; s < N; s += 32) {
-      out_dst[off + s] = load_col<ColT>(g, start + s);
+      if (g.have_col) out_dst[off + s] = load_col<ColT>(g, start + s);
       if (out_center_lid) out_center_lid[off + s] = c;
       if (out_edge_gid) out_edge_gid[off + s] = start + s;
     }
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(csr_ref g,
       }
     }
     if (lane < M) {
-      out_dst[off + lane] = load_col<ColT>(g, start + a);
+      if (g.have_col) out_dst[off + lane] = load_col<ColT>(g, start + a);
       if (out_center_lid) out_center_lid[off + lane] = c;
       if (out_edge_gid) out_edge_gid[off + lane] = start + a;
     }
@@ -219,7 +259,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(csr_ref g,
   }
   for (int i = lane; i < M; i += 32) {
     const int a      = a_s[i];
-    out_dst[off + i] = load_col<ColT>(g, start + a);
+    if (g.have_col) out_dst[off + i] = load_col<ColT>(g, start + a);
     if (out_center_lid) out_center_lid[off + i] = c;
     if (out_edge_gid) out_edge_gid[off + i] = start + a;
   }
@@ -243,13 +283,14 @@ __global__ void large_sample_kernel(csr_ref g,
   if (c >= n) return;
   pcg32 rng;
   rng.init(seed, (uint64_t)(threadIdx.x + (int64_t)blockIdx.x * blockDim.x));
-  const int64_t node  = (int64_t)centers[c];
-  const int64_t start = load_row_ptr(g, node);
-  const int N         = (int)(load_row_ptr(g, node + 1) - start);
-  const int off       = offsets[c];
+  const int64_t node = (int64_t)centers[c];
+  int64_t start = 0, row_end = 0;
+  node_bounds(g, c, n, node, &start, &row_end);
+  const int N   = (int)(row_end - start);
+  const int off = offsets[c];
   if (N <= k) {
     for (int s = threadIdx.x; s < N; s += blockDim.x) {
-      out_dst[off + s] = load_col<ColT>(g, start + s);
+      if (g.have_col) out_dst[off + s] = load_col<ColT>(g, start + s);
       if (out_center_lid) out_center_lid[off + s] = c;
       if (out_edge_gid) out_edge_gid[off + s] = start + s;
     }
@@ -268,14 +309,15 @@ __global__ void large_sample_kernel(csr_ref g,
   __syncthreads();
   for (int s = threadIdx.x; s < k; s += blockDim.x) {
     int nb           = slot[s];
-    out_dst[off + s] = load_col<ColT>(g, start + nb);
+    if (g.have_col) out_dst[off + s] = load_col<ColT>(g, start + nb);
     if (out_edge_gid) out_edge_gid[off + s] = start + nb;
   }
 }
 
 template <typename IdT, typename ColT>
 void run_sampler(const csr_ref& g, const void* centers, int n, int k, uint64_t seed, int* offsets, wholememory_dtype_t col_dtype,
-                 void* dst_ctx, void* lid_ctx, void* gid_ctx, wholememory_env_func_t* env, cudaStream_t s)
+                 void* dst_ctx, void* lid_ctx, void* gid_ctx, wholememory_env_func_t* env, cudaStream_t s,
+                 const std::function<void(const int64_t* edge_ids, void* dst, int total)>& fetch_col = nullptr)
 {
   const IdT* cen = static_cast<const IdT*>(centers);
   temp_buffer counts_b(env), cub_b(env);
@@ -292,13 +334,20 @@ void run_sampler(const csr_ref& g, const void* centers, int n, int k, uint64_t s
   ColT* out_dst   = static_cast<ColT*>(output_alloc(env, dst_ctx, (size_t)total, col_dtype));
   int* out_lid    = lid_ctx ? static_cast<int*>(output_alloc(env, lid_ctx, (size_t)total, WHOLEMEMORY_DT_INT)) : nullptr;
   int64_t* out_gid = gid_ctx ? static_cast<int64_t*>(output_alloc(env, gid_ctx, (size_t)total, WHOLEMEMORY_DT_INT64)) : nullptr;
-  if (n == 0 || total == 0) return;
+  temp_buffer gid_tmp(env);
+  if (!g.have_col && out_gid == nullptr) /* exchange mode always needs the edge ids: they drive the col_idx fetch */
+    out_gid = static_cast<int64_t*>(gid_tmp.device((size_t)std::max(total, 1), WHOLEMEMORY_DT_INT64));
+  if (n == 0 || total == 0) {
+    if (fetch_col) fetch_col(out_gid, out_dst, 0); /* the exchange is collective: take part even with nothing to fetch */
+    return;
+  }
 
   if (k > 1024) {
     temp_buffer scratch_b(env);
     int* scratch = static_cast<int*>(scratch_b.device((size_t)total, WHOLEMEMORY_DT_INT));
     large_sample_kernel<IdT, ColT><<<n, 32, 0, s>>>(g, cen, n, k, seed, offsets, out_dst, out_lid, out_gid, scratch);
     WM_CUDA(cudaGetLastError());
+    if (fetch_col) fetch_col(out_gid, out_dst, total);
     WM_CUDA(cudaStreamSynchronize(s));
     return;
   }
@@ -310,6 +359,7 @@ void run_sampler(const csr_ref& g, const void* centers, int n, int k, uint64_t s
   sample_kernel<IdT, ColT><<<(n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, smem, s>>>(
     g, cen, n, k, ref_block_dim, seed, offsets, out_dst, out_lid, out_gid);
   WM_CUDA(cudaGetLastError());
+  if (fetch_col) fetch_col(out_gid, out_dst, total); /* exchange mode: col_idx[edge id] via the bucket exchange */
   WM_CUDA(cudaStreamSynchronize(s)); /* reference func.cuh:474; temporaries are released on return */
 }
 
@@ -350,23 +400,52 @@ wholememory_error_code_t wholegraph_csr_unweighted_sample_without_replacement(wh
     WM_EXPECT(nd.dtype == WHOLEMEMORY_DT_INT || nd.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR, "center dtype must be int32/int64");
     WM_EXPECT(od.sizes[0] == nd.sizes[0] + 1, WHOLEMEMORY_INVALID_INPUT, "output_sample_offset must have center_count + 1 entries");
     WM_EXPECT(nd.sizes[0] < ((int64_t)1 << 31) - 1, WHOLEMEMORY_INVALID_VALUE, "too many center nodes");
-    for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor})
-      WM_EXPECT(!t->is_wm || handle_is_addressable(t->handle), WHOLEMEMORY_NOT_IMPLEMENTED,
-                "sampling from DISTRIBUTED memory without peer mapping is not built (SURVEY 8(f) rank 2)");
-    csr_ref g{};
-    g.row_ptr              = make_table_ref(wm_csr_row_ptr_tensor);
-    g.col                  = make_table_ref(wm_csr_col_ptr_tensor);
-    g.row_ptr_offset_bytes = rd.storage_offset * 8;
-    g.col_offset_bytes     = cd.storage_offset * (int64_t)wholememory_dtype_get_element_size(cd.dtype);
-    const void* centers    = wholememory_tensor_get_data_pointer(center_nodes_tensor);
-    int* offsets           = static_cast<int*>(wholememory_tensor_get_data_pointer(output_sample_offset_tensor));
+    const void* centers = wholememory_tensor_get_data_pointer(center_nodes_tensor);
+    int* offsets        = static_cast<int*>(wholememory_tensor_get_data_pointer(output_sample_offset_tensor));
     WM_EXPECT(offsets != nullptr && (centers != nullptr || nd.sizes[0] == 0), WHOLEMEMORY_INVALID_INPUT, "null center / offset pointer");
-    auto s       = static_cast<cudaStream_t>(stream);
-    const int n  = (int)nd.sizes[0];
+    auto s          = static_cast<cudaStream_t>(stream);
+    const int n     = (int)nd.sizes[0];
     const bool id64 = nd.dtype == WHOLEMEMORY_DT_INT64, col64 = cd.dtype == WHOLEMEMORY_DT_INT64;
+    const bool row_direct = !wm_csr_row_ptr_tensor->is_wm || handle_is_addressable(wm_csr_row_ptr_tensor->handle);
+    const bool col_direct = !wm_csr_col_ptr_tensor->is_wm || handle_is_addressable(wm_csr_col_ptr_tensor->handle);
+    csr_ref g{};
+    g.have_col = col_direct ? 1 : 0;
+    if (row_direct) {
+      g.row_ptr              = make_table_ref(wm_csr_row_ptr_tensor);
+      g.row_ptr_offset_bytes = rd.storage_offset * 8;
+    }
+    if (col_direct) {
+      g.col              = make_table_ref(wm_csr_col_ptr_tensor);
+      g.col_offset_bytes = cd.storage_offset * (int64_t)wholememory_dtype_get_element_size(cd.dtype);
+    }
+    /* DISTRIBUTED memory without peer mapping (reference ..._nccl_func.cuh:193-387): fetch the row_ptr pairs through the
+     * bucket exchange first, sample edge ids locally, then fetch col_idx[edge id] through the exchange.  Collective. */
+    temp_buffer bounds_ids(p_env_fns), bounds_vals(p_env_fns);
+    if (!row_direct) {
+      auto* ids  = static_cast<int64_t*>(bounds_ids.device((size_t)std::max(2 * n, 1), WHOLEMEMORY_DT_INT64));
+      auto* vals = static_cast<int64_t*>(bounds_vals.device((size_t)std::max(2 * n, 1), WHOLEMEMORY_DT_INT64));
+      if (n > 0) {
+        if (id64) bounds_index_kernel<int64_t><<<(n + 255) / 256, 256, 0, s>>>(static_cast<const int64_t*>(centers), n, ids);
+        else bounds_index_kernel<int32_t><<<(n + 255) / 256, 256, 0, s>>>(static_cast<const int32_t*>(centers), n, ids);
+      }
+      int64_t tsz[2] = {rd.sizes[0], 1}, osz[2] = {2 * (int64_t)n, 1};
+      gather_by_exchange(wm_csr_row_ptr_tensor->handle, wholememory_create_matrix_desc(tsz, 1, rd.storage_offset, WHOLEMEMORY_DT_INT64), ids,
+                         wholememory_create_array_desc(2 * (int64_t)n, 0, WHOLEMEMORY_DT_INT64), vals,
+                         wholememory_create_matrix_desc(osz, 1, 0, WHOLEMEMORY_DT_INT64), p_env_fns, s, -1);
+      g.pre_bounds = vals;
+    }
+    std::function<void(const int64_t*, void*, int)> fetch_col;
+    if (!col_direct) {
+      fetch_col = [&](const int64_t* edge_ids, void* dst, int total) {
+        int64_t tsz[2] = {cd.sizes[0], 1}, osz[2] = {(int64_t)total, 1};
+        gather_by_exchange(wm_csr_col_ptr_tensor->handle, wholememory_create_matrix_desc(tsz, 1, cd.storage_offset, cd.dtype), edge_ids,
+                           wholememory_create_array_desc((int64_t)total, 0, WHOLEMEMORY_DT_INT64), dst,
+                           wholememory_create_matrix_desc(osz, 1, 0, cd.dtype), p_env_fns, s, -1);
+      };
+    }
 #define WM_RUN(IdT, ColT)                                                                                                   \
   run_sampler<IdT, ColT>(g, centers, n, max_sample_count, random_seed, offsets, cd.dtype, output_dest_memory_context,       \
-                         output_center_localid_memory_context, output_edge_gid_memory_context, p_env_fns, s)
+                         output_center_localid_memory_context, output_edge_gid_memory_context, p_env_fns, s, fetch_col)
     if (id64 && col64) WM_RUN(int64_t, int64_t);
     else if (id64) WM_RUN(int64_t, int32_t);
     else if (col64) WM_RUN(int32_t, int64_t);

@@ -10,3 +10,4 @@ from .embedding import (WholeMemoryEmbedding, WholeMemoryEmbeddingModule, WholeM
                         destroy_embedding, destroy_wholememory_cache_policy, destroy_wholememory_optimizer)
 from .wholegraph_ops import generate_random_positive_int_cpu, unweighted_sample_without_replacement  # noqa: E402
 from .graph_ops import add_csr_self_loop, append_unique  # noqa: E402
+from .graph_structure import GraphStructure  # noqa: E402
