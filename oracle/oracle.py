@@ -26,8 +26,8 @@ INT_DTS = (DT_INT, DT_INT64, DT_INT16, DT_INT8)
 
 def build():
     """Compile the C oracle (gcc, a second or two)."""
-    src = os.path.join(_HERE, "wm_oracle.c")
-    if os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("wm_oracle.c", "wm_oracle_weighted.c")]
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -59,6 +59,9 @@ def lib():
         _lib.oracle_unweighted_sample.argtypes = [vp, vp, vp, i64, ci, ctypes.c_uint64, vp, vp, vp, vp]
         _lib.oracle_unweighted_sample.restype = i64
         _lib.oracle_gather_mt.argtypes = [vp, i64, i64, vp, i64, vp, i64, ci]
+        _lib.oracle_exponential_negative_floats.argtypes = [ctypes.c_uint64, ctypes.c_uint64, vp, i64]
+        _lib.oracle_weighted_sample.argtypes = [vp, vp, vp, ci, vp, i64, ci, ctypes.c_uint64, vp, vp, vp, vp, vp]
+        _lib.oracle_weighted_sample.restype = i64
     return _lib
 
 
@@ -232,6 +235,33 @@ def unweighted_sample(row_ptr, col, centers, k, seed):
     gid = np.zeros(total, dtype=np.int64)
     lib().oracle_unweighted_sample(_p(row_ptr), _p(col), _p(centers), n, k, seed, _p(offsets), _p(dst), _p(lid), _p(gid))
     return offsets, dst, lid, gid
+
+
+def exponential_negative_floats(seed, subsequence, count):
+    out = np.zeros(count, dtype=np.float32)
+    lib().oracle_exponential_negative_floats(seed, subsequence, _p(out), count)
+    return out
+
+
+def weighted_sample(row_ptr, col, weights, centers, k, seed):
+    """Returns (offsets, dst, center_local, edge_gid, margin) -- margin[c] = relative gap between the k-th and (k+1)-th
+    best key of center c (inf when every neighbour is taken): a tiny margin marks a last-ulp tie."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    is_float = 1 if weights.dtype == np.float32 else 0
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    centers = np.ascontiguousarray(centers, dtype=np.int64)
+    n = centers.shape[0]
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    total = lib().oracle_weighted_sample(_p(row_ptr), _p(col), _p(w), is_float, _p(centers), n, k, seed, _p(offsets), None,
+                                         None, None, None)
+    dst = np.zeros(total, dtype=np.int64)
+    lid = np.zeros(total, dtype=np.int32)
+    gid = np.zeros(total, dtype=np.int64)
+    margin = np.zeros(n, dtype=np.float32)
+    lib().oracle_weighted_sample(_p(row_ptr), _p(col), _p(w), is_float, _p(centers), n, k, seed, _p(offsets), _p(dst), _p(lid),
+                                 _p(gid), _p(margin))
+    return offsets, dst, lid, gid, margin
 
 
 # ---------------------------------------------------------------- timed CPU baseline

@@ -270,7 +270,58 @@ def scenario_file_io(rank, world, comm):
             os.remove(f)
 
 
-SCENARIOS = {"file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+def scenario_weighted_sampling(rank, world, comm):
+    """Weighted (A-Res) sampler vs the oracle: same sample sets for the same seed.  Keys are float log1pf/exp2f values, so a
+    center whose k-th and (k+1)-th keys are within a few ulp may legitimately resolve differently between libm and CUDA:
+    those (flagged by the oracle's margin) are only required to be valid samples."""
+    import torch
+    import wholegraph_b200.binding as wmb
+    import wholegraph_b200.torch as wgth
+    from oracle import oracle as O
+    rng = np.random.default_rng(4242)
+    nodes = 3000
+    deg = np.minimum(rng.zipf(1.4, size=nodes), 700) + rng.integers(0, 20, size=nodes)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    edges = int(row_ptr[-1])
+    col = rng.integers(0, nodes, size=edges).astype(np.int64)
+    for w_np, w_wm in ((np.float32, wmb.DtFloat), (np.float64, wmb.DtDouble)):
+        weights = rng.uniform(0.05, 4.0, size=edges).astype(w_np)
+        for mt in (wmb.MtChunked, wmb.MtContinuous):
+            rp = wmb.create_wholememory_array(wmb.DtInt64, nodes + 1, comm.wmb_comm, mt, wmb.MlDevice)
+            cp = wmb.create_wholememory_array(wmb.DtInt64, edges, comm.wmb_comm, mt, wmb.MlDevice)
+            wp = wmb.create_wholememory_array(w_wm, edges, comm.wmb_comm, mt, wmb.MlDevice)
+            for t, host, dt in ((rp, row_ptr, wmb.DtInt64), (cp, col, wmb.DtInt64), (wp, weights, w_wm)):
+                loc, first = t.get_wholememory_handle().get_local_flatten_tensor(dt, wmb.MlDevice, torch.cuda.current_device())
+                loc.copy_(torch.from_numpy(host[first:first + loc.numel()]))
+            comm.barrier()
+            crng = np.random.default_rng(11 + rank)
+            for k in (5, 10, 25, 32, 40, 300, -1):
+                centers = crng.integers(0, nodes, size=301).astype(np.int64)
+                seed = 99 + k
+                res = wgth.weighted_sample_without_replacement(rp, cp, wp, torch.from_numpy(centers).cuda(), k, random_seed=seed,
+                                                               need_center_local_output=True, need_edge_output=True)
+                eo, ed, el, eg, margin = O.weighted_sample(row_ptr, col, weights, centers, k, seed)
+                off = res[0].cpu().numpy()
+                assert off.tolist() == eo.tolist(), f"offsets k={k}"
+                dst, lid, gid = res[1].cpu().numpy(), res[2].cpu().numpy(), res[3].cpu().numpy()
+                assert lid.tolist() == el.tolist()
+                loose = 0
+                for c in range(centers.size):
+                    s, e = off[c], off[c + 1]
+                    lo, hi = row_ptr[centers[c]], row_ptr[centers[c] + 1]
+                    assert np.all((gid[s:e] >= lo) & (gid[s:e] < hi)) and len(set(gid[s:e].tolist())) == e - s
+                    assert np.array_equal(dst[s:e], col[gid[s:e]])
+                    if set(gid[s:e].tolist()) != set(eg[s:e].tolist()):
+                        assert margin[c] < 1e-5, f"center {c} (k={k}): different sample set with key margin {margin[c]}"
+                        assert len(set(gid[s:e].tolist()) ^ set(eg[s:e].tolist())) <= 2
+                        loose += 1
+                assert loose <= 3, f"{loose} centers resolved near-ties differently (k={k})"
+            comm.barrier()
+            for t in (rp, cp, wp):
+                wmb.destroy_wholememory_tensor(t)
+
+
+SCENARIOS = {"weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):

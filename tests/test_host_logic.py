@@ -182,15 +182,26 @@ def test_optimizer_parameter_names(wmb):
 
 def test_out_of_scope_entry_points_say_so(wmb):
     L = _lib.lib
+    # every op diagnoses null arguments instead of crashing
     assert L.wholegraph_csr_weighted_sample_without_replacement(None, None, None, None, 5, None, None, None, None, 0, None,
-                                                                None) == wmb.WholeMemoryErrorCode.NotImplemented
-    assert L.generate_exponential_distribution_negative_float_cpu(0, 0, None) == wmb.WholeMemoryErrorCode.NotImplemented
-    # built ops diagnose null arguments instead of crashing
+                                                                None) == wmb.WholeMemoryErrorCode.InvalidInput
+    assert L.generate_exponential_distribution_negative_float_cpu(0, 0, None) == wmb.WholeMemoryErrorCode.InvalidInput
     assert L.wholememory_load_from_file(None, 0, 0, 0, None, 0, 0) == wmb.WholeMemoryErrorCode.InvalidInput
     assert L.graph_append_unique(None, None, None, None, None, None) == wmb.WholeMemoryErrorCode.InvalidInput
     assert L.csr_add_self_loop(None, None, None, None, None) == wmb.WholeMemoryErrorCode.InvalidInput
     with pytest.raises(ValueError):
         wmb.create_cache_policy(wmb.PyWholeMemoryComm(None), wmb.MtChunked, wmb.MlDevice, wmb.AtReadOnly, 2.0)
+
+
+def test_host_key_stream_matches_oracle(wmb, oracle):
+    """generate_exponential_distribution_negative_float_cpu: log2(u) keys of weight 1, all negative, oracle-identical."""
+    import torch
+    from wholegraph_b200.torch.wholegraph_env import wrap_torch_tensor
+    out = torch.zeros(64, dtype=torch.float32)
+    wmb.host_generate_exponential_distribution_negative_float(1234, 7, wrap_torch_tensor(out))
+    exp = oracle.exponential_negative_floats(1234, 7, 64)
+    assert out.numpy().tobytes() == exp.tobytes()
+    assert (out < 0).all() and torch.isfinite(out).all()
 
 
 def test_host_random_stream_matches_oracle(wmb, oracle):

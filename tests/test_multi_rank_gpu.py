@@ -41,7 +41,7 @@ def _run(world, scenario, env=None, share_gpu=False):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("scenario", ["gather_scatter", "gradient", "sampling", "file_io"])
+@pytest.mark.parametrize("scenario", ["gather_scatter", "gradient", "sampling", "file_io", "weighted_sampling"])
 def test_single_rank(scenario):
     _run(1, scenario)
 
@@ -55,7 +55,7 @@ def test_single_rank_forced_bucket_exchange(scenario):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("scenario", ["gather_scatter", "sampling", "file_io"])
+@pytest.mark.parametrize("scenario", ["gather_scatter", "sampling", "file_io", "weighted_sampling"])
 def test_ranks_sharing_one_gpu_mapped_memory(world, scenario):
     """Cross-process VMM mapping (POSIX fd over AF_UNIX), partitions, peer addressing -- no NCCL needed."""
     _run(world, scenario, share_gpu=True)

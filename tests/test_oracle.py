@@ -261,3 +261,38 @@ def test_unweighted_sample_structure():
                 assert np.array_equal(gid[s:e], np.arange(lo, hi))  # CSR order when everything is taken
     off, dst, lid, gid = O.unweighted_sample(row_ptr, col, centers, -1, 1)
     assert np.array_equal(np.diff(off), deg[centers])
+
+
+def test_weighted_sample_oracle_structure_and_bias():
+    """A-Res restatement: samples are distinct neighbours; heavy edges are kept far more often than light ones."""
+    rng = np.random.default_rng(21)
+    nodes = 200
+    deg = rng.integers(0, 90, size=nodes)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, nodes, size=int(row_ptr[-1])).astype(np.int64)
+    w = rng.uniform(0.1, 1.0, size=col.size).astype(np.float32)
+    heavy = rng.random(col.size) < 0.1
+    w[heavy] = 50.0
+    centers = rng.integers(0, nodes, size=300).astype(np.int64)
+    kept_heavy = kept_light = tot_heavy = tot_light = 0
+    for k, seed in ((10, 1), (25, 2), (40, 3)):
+        off, dst, lid, gid, margin = O.weighted_sample(row_ptr, col, w, centers, k, seed)
+        assert np.array_equal(np.diff(off), np.minimum(deg[centers], k))
+        for c, node in enumerate(centers):
+            s, e = off[c], off[c + 1]
+            lo, hi = row_ptr[node], row_ptr[node + 1]
+            assert np.all(lid[s:e] == c) and np.all((gid[s:e] >= lo) & (gid[s:e] < hi)) and len(set(gid[s:e].tolist())) == e - s
+            assert np.array_equal(dst[s:e], col[gid[s:e]])
+            if deg[node] <= k:
+                assert np.array_equal(gid[s:e], np.arange(lo, hi)) and np.isinf(margin[c])
+            else:
+                sel = np.zeros(hi - lo, bool)
+                sel[gid[s:e] - lo] = True
+                hv = heavy[lo:hi]
+                kept_heavy += int((sel & hv).sum()); tot_heavy += int(hv.sum())
+                kept_light += int((sel & ~hv).sum()); tot_light += int((~hv).sum())
+    assert kept_heavy / max(tot_heavy, 1) > 2.0 * kept_light / max(tot_light, 1)
+    # the key stream: log2(u)/w, negative, and the weight-1 helper equals the k-stream of a unit-weight edge
+    keys = O.exponential_negative_floats(5, 0, 1000)
+    assert np.all(keys < 0) and np.all(np.isfinite(keys))
+    assert abs(float(np.mean(keys)) + 1.0 / np.log(2.0)) < 0.15  # E[log2 U] = -1/ln 2

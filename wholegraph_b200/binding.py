@@ -655,6 +655,22 @@ def csr_unweighted_sample_without_replacement(wm_csr_row_ptr_tensor, wm_csr_col_
         _env_ptr(p_env_fns_int), c_void_p(stream_int)))
 
 
+def csr_weighted_sample_without_replacement(wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor,
+                                            center_nodes_tensor, max_sample_count, output_sample_offset_tensor,
+                                            output_dest_memory_handle, output_center_localid_memory_handle,
+                                            output_edge_gid_memory_handle, random_seed, p_env_fns_int, stream_int):
+    _chk(lib.wholegraph_csr_weighted_sample_without_replacement(
+        wm_csr_row_ptr_tensor.wholememory_tensor, wm_csr_col_ptr_tensor.wholememory_tensor,
+        wm_csr_weight_ptr_tensor.wholememory_tensor, c_void_p(center_nodes_tensor.get_c_handle()), max_sample_count,
+        c_void_p(output_sample_offset_tensor.get_c_handle()), c_void_p(output_dest_memory_handle),
+        c_void_p(output_center_localid_memory_handle), c_void_p(output_edge_gid_memory_handle), random_seed,
+        _env_ptr(p_env_fns_int), c_void_p(stream_int)))
+
+
+def host_generate_exponential_distribution_negative_float(random_seed, sub_sequence, output):
+    _chk(lib.generate_exponential_distribution_negative_float_cpu(random_seed, sub_sequence, c_void_p(output.get_c_handle())))
+
+
 def append_unique(target_node_tensor, neighbor_node_tensor, output_unique_node_memory_handle,
                   output_neighbor_raw_to_unique_mapping_tensor, p_env_fns_int, stream_int):
     _chk(lib.graph_append_unique(c_void_p(target_node_tensor.get_c_handle()), c_void_p(neighbor_node_tensor.get_c_handle()),

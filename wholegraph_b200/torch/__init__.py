@@ -8,6 +8,7 @@ from .tensor import (WholeMemoryTensor, create_wholememory_tensor, create_wholem
 from .embedding import (WholeMemoryEmbedding, WholeMemoryEmbeddingModule, WholeMemoryOptimizer,  # noqa: E402
                         create_embedding, create_wholememory_cache_policy, create_wholememory_optimizer,
                         destroy_embedding, destroy_wholememory_cache_policy, destroy_wholememory_optimizer)
-from .wholegraph_ops import generate_random_positive_int_cpu, unweighted_sample_without_replacement  # noqa: E402
+from .wholegraph_ops import (generate_exponential_distribution_negative_float_cpu, generate_random_positive_int_cpu,  # noqa: E402
+                             unweighted_sample_without_replacement, weighted_sample_without_replacement)
 from .graph_ops import add_csr_self_loop, append_unique  # noqa: E402
 from .graph_structure import GraphStructure  # noqa: E402

@@ -47,12 +47,19 @@ class GraphStructure(object):
                                                                     center_nodes_tensor, max_sample_count, random_seed,
                                                                     need_center_local_output, need_edge_output)
 
+    def weighted_sample_without_replacement_one_hop(self, weight_name: str, center_nodes_tensor: torch.Tensor, max_sample_count: int, *,
+                                                    random_seed: Union[int, None] = None,
+                                                    need_center_local_output: bool = False, need_edge_output: bool = False):
+        assert weight_name in self.edge_attributes
+        weight_tensor = self.edge_attributes[weight_name]
+        return wholegraph_ops.weighted_sample_without_replacement(self.csr_row_ptr.wmb_tensor, self.csr_col_ind.wmb_tensor,
+                                                                  weight_tensor.wmb_tensor, center_nodes_tensor, max_sample_count,
+                                                                  random_seed, need_center_local_output, need_edge_output)
+
     def multilayer_sample_without_replacement(self, node_ids: torch.Tensor, max_neighbors: List[int],
                                               weight_name: Union[str, None] = None, random_seed: Union[int, None] = None):
         """fanout list consumed front-to-back from the seeds (reference graph_structure.py:160-180).
         Returns (target_gids[hops+1], edge_indice[hops], csr_row_ptr[hops], csr_col_ind[hops])."""
-        if weight_name is not None:
-            raise NotImplementedError("weighted sampling is not built yet (SURVEY 8(f) rank 4)")
         hops = len(max_neighbors)
         edge_indice = [None] * hops
         csr_row_ptr = [None] * hops
@@ -61,8 +68,12 @@ class GraphStructure(object):
         target_gids[hops] = node_ids
         for i in range(hops - 1, -1, -1):
             seed = None if random_seed is None else random_seed + i
-            neighbor_gids_offset, neighbor_gids_vdata, neighbor_src_lids = self.unweighted_sample_without_replacement_one_hop(
-                target_gids[i + 1], max_neighbors[hops - i - 1], random_seed=seed, need_center_local_output=True)
+            if weight_name is None:
+                neighbor_gids_offset, neighbor_gids_vdata, neighbor_src_lids = self.unweighted_sample_without_replacement_one_hop(
+                    target_gids[i + 1], max_neighbors[hops - i - 1], random_seed=seed, need_center_local_output=True)
+            else:
+                neighbor_gids_offset, neighbor_gids_vdata, neighbor_src_lids = self.weighted_sample_without_replacement_one_hop(
+                    weight_name, target_gids[i + 1], max_neighbors[hops - i - 1], random_seed=seed, need_center_local_output=True)
             unique_gids, neighbor_raw_to_unique_mapping = graph_ops.append_unique(target_gids[i + 1], neighbor_gids_vdata,
                                                                                   need_neighbor_raw_to_unique=True)
             csr_row_ptr[i] = neighbor_gids_offset
