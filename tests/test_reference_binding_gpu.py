@@ -1,6 +1,7 @@
 """Drop-in proof: the REFERENCE's own cython binding (wholememory_binding.pyx, unmodified, cythonized against THIS repo's
 headers and linked to THIS repo's libwholegraph.so by oracle/build_ref_binding.sh) drives the sm_100a kernels.
 The env-function callbacks below are a transcription of what pylibwholegraph/torch/wholegraph_env.py registers."""
+import ctypes
 import glob
 import os
 import sys
@@ -13,6 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIND_DIR = os.path.join(ROOT, "oracle", "_ref", "refbinding")
 HAVE = bool(glob.glob(os.path.join(BIND_DIR, "wholememory_binding*.so")))
+
+
+_IMMORTAL = []
 
 
 class _Ctx(object):
@@ -56,6 +60,12 @@ def test_reference_cython_binding_on_our_library():
     gctx = object()
     env = rwmb.GlobalContextWrapper()
     env.create_context(create_ctx, destroy_ctx, malloc_fn, free_fn, gctx, malloc_fn, free_fn, gctx)
+    # The reference keeps its GlobalContextWrapper in a module global for the life of the process
+    # (torch/wholegraph_env.py:29-40); its __dealloc__ (wholememory_binding.pyx:387-397) raises inside tp_dealloc
+    # ("no attribute 'self'"), and pytest's unraisable-exception hook then holds a dangling object -> SIGSEGV at
+    # session end.  Same lifetime here: never collected.
+    _IMMORTAL.append(env)
+    ctypes.pythonapi.Py_IncRef(ctypes.py_object(env))
 
     def wrap(t):
         d = rwmb.PyWholeMemoryTensorDescription()

@@ -11,11 +11,12 @@
  * duplicate gradients in arrival order) is kept identical so results match the reference's.
  *
  * Design: received (row id, position) pairs are radix-sorted by row id (stable => arrival order
- * inside a run).  The kernel is launched with one CTA per SORTED POSITION; a CTA whose position is
- * not the head of a run exits at once, a head CTA walks its run, summing the gradient rows in
- * registers, and then applies the optimizer to W / state in place.  No unique-count is needed on
- * the host (no D2H sync), no deduplicated gradient matrix is written or re-read, and the row of W
- * is touched by exactly one kernel.  Rows are moved as float4 when alignment allows.
+ * inside a run).  The kernel is launched with one WARP per SORTED POSITION (8 per CTA); a warp whose
+ * position is not the head of a run exits at once, a head warp issues every load of its row (gradient,
+ * W, state) before the first use, walks its run summing duplicate gradient rows in registers, and then
+ * applies the optimizer to W / state in place.  No unique-count is needed on the host (no D2H sync),
+ * no deduplicated gradient matrix is written or re-read, and the row of W is touched by exactly one
+ * kernel.  Rows are moved as float4 when alignment allows.
  * Roofline: per unique row  read g*dups + W + state, write W + state  (7*D*4+16 B for LazyAdam,
  * D=512 -> 14,352 B), all local HBM.
  */
@@ -61,18 +62,73 @@ __global__ void iota_kernel(int* p, int n)
   if (i < n) p[i] = i;
 }
 
-template <typename IdxT, int OPT, int VEC>
-__global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __restrict__ sorted_idx,
-                                                                const int* __restrict__ sorted_pos,
-                                                                int n,
-                                                                const float* __restrict__ grads,
-                                                                int64_t grad_stride,
-                                                                optimizer_rows rows,
-                                                                optimizer_params p,
-                                                                float lr)
+/* One optimizer step on VEC consecutive elements of a row.  Expression order follows the reference kernels
+ * (embedding_optimizer_func.cu:178-224 SGD, :331-419 LazyAdam, :594-657 AdaGrad, :791-851 RMSProp) so results match bit for bit. */
+template <int OPT, int VEC>
+__device__ __forceinline__ void optimizer_step(fvec<VEC>& g, fvec<VEC>& wv, fvec<VEC>& sv0, fvec<VEC>& sv1, const optimizer_params& p,
+                                               float lr, float beta1t, float beta2t)
 {
-  const int b = blockIdx.x;
-  /* four independent loads up front (one DRAM round trip): my id, my neighbours' ids, my gradient position */
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    float grad_value      = g.at(k);
+    float embedding_value = wv.at(k);
+    if (OPT == WHOLEMEMORY_OPT_SGD) {
+      grad_value += p.weight_decay * embedding_value;
+      embedding_value -= lr * grad_value;
+    } else if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) {
+      if (p.adam_w) {
+        embedding_value -= lr * p.weight_decay * embedding_value;
+      } else {
+        grad_value = grad_value + p.weight_decay * embedding_value;
+      }
+      float m         = sv0.at(k);
+      float v         = sv1.at(k);
+      m               = p.beta1 * m + (1 - p.beta1) * grad_value;
+      v               = p.beta2 * v + (1 - p.beta2) * grad_value * grad_value;
+      float mhat      = m / (1 - beta1t);
+      float vhat      = v / (1 - beta2t);
+      embedding_value = embedding_value - lr * mhat / (sqrtf(vhat) + p.epsilon);
+      sv0.at(k)       = m;
+      sv1.at(k)       = v;
+    } else if (OPT == WHOLEMEMORY_OPT_ADAGRAD) {
+      grad_value      = grad_value + p.weight_decay * embedding_value;
+      float state_sum = sv0.at(k);
+      state_sum       = state_sum + grad_value * grad_value;
+      embedding_value = embedding_value - lr * grad_value / (sqrtf(state_sum) + p.epsilon);
+      sv0.at(k)       = state_sum;
+    } else { /* RMSPROP */
+      grad_value      = grad_value + p.weight_decay * embedding_value;
+      float v         = sv0.at(k);
+      v               = p.alpha * v + (1 - p.alpha) * grad_value * grad_value;
+      embedding_value = embedding_value - lr * grad_value / (sqrtf(v) + p.epsilon);
+      sv0.at(k)       = v;
+    }
+    wv.at(k) = embedding_value;
+  }
+}
+
+constexpr int kOptWarps   = 4; /* sorted positions per CTA (one warp each) */
+constexpr int kOptMinCtas = 8; /* <= 64 registers: 32 resident warps per SM */
+
+/* One WARP per sorted position.  Each lane keeps U vectors of every stream (gradient, W, state) in registers, so
+ * U*4 independent 16 B loads per lane are issued before the first use.  Measured on B200 (LazyAdam, 512-float rows,
+ * tools/bench_ops.py, whole call): CTA per position 0.794 ms; warp per position U=4 (96 regs) 0.897, U=2 8-warp CTAs
+ * 0.784, U=1 0.778; U=2 with 4-warp CTAs capped at 64 registers 0.710 <- this configuration.  The step has ~55
+ * instructions per element (three IEEE divides and a square root), so resident warps matter more than loads per lane. */
+template <typename IdxT, int OPT, int VEC, int U>
+__global__ void __launch_bounds__(kOptWarps * 32, kOptMinCtas) fused_merge_update_kernel(const IdxT* __restrict__ sorted_idx,
+                                                                            const int* __restrict__ sorted_pos,
+                                                                            int n,
+                                                                            const float* __restrict__ grads,
+                                                                            int64_t grad_stride,
+                                                                            optimizer_rows rows,
+                                                                            optimizer_params p,
+                                                                            float lr)
+{
+  const int lane = threadIdx.x & 31;
+  const int b    = blockIdx.x * kOptWarps + (threadIdx.x >> 5);
+  if (b >= n) return;
+  /* independent loads up front (one DRAM round trip): my id, my neighbours' ids, my gradient position */
   const IdxT row_id  = sorted_idx[b];
   const IdxT prev_id = b > 0 ? sorted_idx[b - 1] : row_id;
   const IdxT next_id = b + 1 < n ? sorted_idx[b + 1] : row_id;
@@ -85,6 +141,7 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
   float* w  = rows.w + local * rows.w_stride;
   float* s0 = rows.state ? rows.state + local * rows.state_stride : nullptr; /* m | state_sum | v */
   float* s1 = s0 ? s0 + rows.w_stride : nullptr;                             /* LazyAdam v */
+  const float* g0 = grads + (int64_t)pos0 * grad_stride;
 
   float beta1t = 0.f, beta2t = 0.f;
   if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) {
@@ -93,91 +150,72 @@ __global__ void __launch_bounds__(128) fused_merge_update_kernel(const IdxT* __r
     beta2t = rows.b12[local * 2 + 1] * p.beta2;
   }
 
-  for (int c = threadIdx.x * VEC; c < rows.dim; c += blockDim.x * VEC) {
-    /* issue the row's W / state loads first: they do not depend on the gradient chain, so all of the
-     * CTA's DRAM reads are in flight together (measured: this kernel is latency-bound per CTA) */
-    fvec<VEC> wv = ldv<VEC>(w + c);
-    fvec<VEC> sv0, sv1;
-    if (OPT != WHOLEMEMORY_OPT_SGD) sv0 = ldv<VEC>(s0 + c);
-    if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) sv1 = ldv<VEC>(s1 + c);
+  constexpr int kStep = 32 * VEC;
+  for (int c0 = lane * VEC; c0 < rows.dim; c0 += kStep * U) {
+    fvec<VEC> g[U], wv[U], sv0[U], sv1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * kStep;
+      if (c < rows.dim) {
+        g[u]  = ldv<VEC>(g0 + c);
+        wv[u] = ldv<VEC>(w + c);
+        if (OPT != WHOLEMEMORY_OPT_SGD) sv0[u] = ldv<VEC>(s0 + c);
+        if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) sv1[u] = ldv<VEC>(s1 + c);
+      }
+    }
     /* 1. merge duplicates: g = g[pos0] + g[pos1] + ... in arrival order */
-    fvec<VEC> g = ldv<VEC>(grads + (int64_t)pos0 * grad_stride + c);
     if (has_dups) {
       for (int j = b + 1; j < n && sorted_idx[j] == row_id; ++j) {
-        fvec<VEC> o = ldv<VEC>(grads + (int64_t)sorted_pos[j] * grad_stride + c);
+        const float* gj = grads + (int64_t)sorted_pos[j] * grad_stride;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) g.at(k) += o.at(k);
-      }
-    }
-    /* 2. optimizer */
-    if (OPT == WHOLEMEMORY_OPT_SGD) {
+        for (int u = 0; u < U; ++u) {
+          const int c = c0 + u * kStep;
+          if (c < rows.dim) {
+            fvec<VEC> o = ldv<VEC>(gj + c);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float grad_value      = g.at(k);
-        float embedding_value = wv.at(k);
-        grad_value += p.weight_decay * embedding_value;
-        embedding_value -= lr * grad_value;
-        wv.at(k) = embedding_value;
-      }
-    } else if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) {
-      fvec<VEC>& mv = sv0;
-      fvec<VEC>& vv = sv1;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float grad_value      = g.at(k);
-        float embedding_value = wv.at(k);
-        if (p.adam_w) {
-          embedding_value -= lr * p.weight_decay * embedding_value;
-        } else {
-          grad_value = grad_value + p.weight_decay * embedding_value;
+            for (int k = 0; k < VEC; ++k) g[u].at(k) += o.at(k);
+          }
         }
-        float m         = mv.at(k);
-        float v         = vv.at(k);
-        m               = p.beta1 * m + (1 - p.beta1) * grad_value;
-        v               = p.beta2 * v + (1 - p.beta2) * grad_value * grad_value;
-        float mhat      = m / (1 - beta1t);
-        float vhat      = v / (1 - beta2t);
-        embedding_value = embedding_value - lr * mhat / (sqrtf(vhat) + p.epsilon);
-        mv.at(k)        = m;
-        vv.at(k)        = v;
-        wv.at(k)        = embedding_value;
       }
-      stv<VEC>(s0 + c, mv);
-      stv<VEC>(s1 + c, vv);
-    } else if (OPT == WHOLEMEMORY_OPT_ADAGRAD) {
-      fvec<VEC>& sv = sv0;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float grad_value      = g.at(k);
-        float embedding_value = wv.at(k);
-        grad_value            = grad_value + p.weight_decay * embedding_value;
-        float state_sum       = sv.at(k);
-        state_sum             = state_sum + grad_value * grad_value;
-        embedding_value       = embedding_value - lr * grad_value / (sqrtf(state_sum) + p.epsilon);
-        sv.at(k)              = state_sum;
-        wv.at(k)              = embedding_value;
-      }
-      stv<VEC>(s0 + c, sv);
-    } else { /* RMSPROP */
-      fvec<VEC>& vv = sv0;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float grad_value      = g.at(k);
-        float embedding_value = wv.at(k);
-        grad_value            = grad_value + p.weight_decay * embedding_value;
-        float v               = vv.at(k);
-        v                     = p.alpha * v + (1 - p.alpha) * grad_value * grad_value;
-        embedding_value       = embedding_value - lr * grad_value / (sqrtf(v) + p.epsilon);
-        vv.at(k)              = v;
-        wv.at(k)              = embedding_value;
-      }
-      stv<VEC>(s0 + c, vv);
     }
-    stv<VEC>(w + c, wv);
+    /* 2. optimizer, in place */
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * kStep;
+      if (c < rows.dim) {
+        optimizer_step<OPT, VEC>(g[u], wv[u], sv0[u], sv1[u], p, lr, beta1t, beta2t);
+        if (OPT != WHOLEMEMORY_OPT_SGD) stv<VEC>(s0 + c, sv0[u]);
+        if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM) stv<VEC>(s1 + c, sv1[u]);
+        stv<VEC>(w + c, wv[u]);
+      }
+    }
   }
-  if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM && threadIdx.x == 0) {
+  if (OPT == WHOLEMEMORY_OPT_LAZY_ADAM && lane == 0) {
     rows.b12[local * 2 + 0] = beta1t;
     rows.b12[local * 2 + 1] = beta2t;
+  }
+}
+
+template <typename IdxT, int VEC, int U>
+void launch_fused_u(int opt, const IdxT* si, const int* sp, int n, const float* g, int64_t gs, const optimizer_rows& rows,
+                    const optimizer_params& p, float lr, cudaStream_t s)
+{
+  const unsigned grid = (unsigned)((n + kOptWarps - 1) / kOptWarps);
+  const unsigned cta  = kOptWarps * 32;
+  switch (opt) {
+    case WHOLEMEMORY_OPT_SGD:
+      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_SGD, VEC, U><<<grid, cta, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
+      break;
+    case WHOLEMEMORY_OPT_LAZY_ADAM:
+      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_LAZY_ADAM, VEC, U><<<grid, cta, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
+      break;
+    case WHOLEMEMORY_OPT_ADAGRAD:
+      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_ADAGRAD, VEC, U><<<grid, cta, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
+      break;
+    case WHOLEMEMORY_OPT_RMSPROP:
+      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_RMSPROP, VEC, U><<<grid, cta, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
+      break;
+    default: WM_THROW(WHOLEMEMORY_INVALID_INPUT, "unknown optimizer type %d", opt);
   }
 }
 
@@ -185,21 +223,8 @@ template <typename IdxT, int VEC>
 void launch_fused(int opt, const IdxT* si, const int* sp, int n, const float* g, int64_t gs, const optimizer_rows& rows,
                   const optimizer_params& p, float lr, cudaStream_t s)
 {
-  switch (opt) {
-    case WHOLEMEMORY_OPT_SGD:
-      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_SGD, VEC><<<n, 128, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
-      break;
-    case WHOLEMEMORY_OPT_LAZY_ADAM:
-      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_LAZY_ADAM, VEC><<<n, 128, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
-      break;
-    case WHOLEMEMORY_OPT_ADAGRAD:
-      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_ADAGRAD, VEC><<<n, 128, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
-      break;
-    case WHOLEMEMORY_OPT_RMSPROP:
-      fused_merge_update_kernel<IdxT, WHOLEMEMORY_OPT_RMSPROP, VEC><<<n, 128, 0, s>>>(si, sp, n, g, gs, rows, p, lr);
-      break;
-    default: WM_THROW(WHOLEMEMORY_INVALID_INPUT, "unknown optimizer type %d", opt);
-  }
+  if (rows.dim > 32 * VEC) launch_fused_u<IdxT, VEC, 2>(opt, si, sp, n, g, gs, rows, p, lr, s);
+  else launch_fused_u<IdxT, VEC, 1>(opt, si, sp, n, g, gs, rows, p, lr, s);
 }
 
 template <typename IdxT>
