@@ -1,6 +1,6 @@
 /*
  * Graph helper ops that sit between sampling hops (reference cpp/include/wholememory/graph_op.h:39-59).
- * SURVEY section 8(f) "next" rows; until built they return WHOLEMEMORY_NOT_IMPLEMENTED.
+ * Implementation: wholegraph_b200/csrc/graph_ops.cu (first-occurrence-ordered append-unique, CSR self-loop insert).
  */
 #pragma once
 #include <cuda_runtime_api.h>

@@ -5,8 +5,8 @@
  * Implementation: wholegraph_b200/csrc/{runtime,communicator,memory_handle}.cpp.
  *
  * Scope of this build: ONE NVSwitch box, one process per GPU.  Multi-node,
- * MNNVL cliques, HIERARCHY memory, NVSHMEM and file I/O are out of scope; their entry points
- * exist and return WHOLEMEMORY_NOT_IMPLEMENTED / NOT_SUPPORTED.
+ * MNNVL cliques, HIERARCHY memory and NVSHMEM are out of scope; their entry points exist and
+ * return WHOLEMEMORY_NOT_IMPLEMENTED / NOT_SUPPORTED.
  */
 #pragma once
 #include <stdio.h>
@@ -189,7 +189,7 @@ wholememory_error_code_t wholememory_get_rank_partition_offsets(
 /* GPU count probed in a forked child so the caller never creates a CUDA context */
 int fork_get_device_count();
 
-/* checkpoint I/O: out of scope this round => WHOLEMEMORY_NOT_IMPLEMENTED (reference :448-470) */
+/* part-file load / store (reference :448-470; wholegraph_b200/csrc/file_io.cpp).  round_robin_size != 0 is refused. */
 wholememory_error_code_t wholememory_load_from_file(wholememory_handle_t wholememory_handle,
                                                     size_t memory_offset,
                                                     size_t memory_entry_size,

@@ -120,12 +120,13 @@ def scenario_gradient(rank, world, comm):
             all_idx, all_g = [], []
             for r in range(world):
                 rr = np.random.default_rng(9000 + ci * 100 + step * 10 + r)
-                n = 700 + 13 * r
+                n = (6000 if (ci == 0 and step == 2) else 700) + 13 * r  # the big step outgrows the first gradient stage
                 idx_r = (rr.zipf(1.3, size=n) % rows).astype(np.int64)  # heavy duplication
                 g_r = rr.standard_normal((n, dim)).astype(np.float32)
                 all_idx.append(idx_r)
                 all_g.append(g_r)
-            emb.add_gradients(torch.from_numpy(all_idx[rank]).cuda(), torch.from_numpy(all_g[rank]).cuda())
+            my_idx = all_idx[rank].astype(np.int32 if step == 1 else np.int64)
+            emb.add_gradients(torch.from_numpy(my_idx).cuda(), torch.from_numpy(all_g[rank]).cuda())
             emb.need_apply = True
             opt.step(0.01)
             urows, ug = O.dedup_gradients(np.concatenate(all_idx), np.concatenate(all_g))

@@ -55,9 +55,10 @@ def test_single_rank_forced_bucket_exchange(scenario):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("scenario", ["gather_scatter", "sampling", "file_io", "weighted_sampling"])
+@pytest.mark.parametrize("scenario", ["gather_scatter", "gradient", "sampling", "file_io", "weighted_sampling"])
 def test_ranks_sharing_one_gpu_mapped_memory(world, scenario):
-    """Cross-process VMM mapping (POSIX fd over AF_UNIX), partitions, peer addressing -- no NCCL needed."""
+    """Cross-process VMM mapping (POSIX fd over AF_UNIX), partitions, peer addressing, peer-store gradient push --
+    no NCCL needed."""
     _run(world, scenario, share_gpu=True)
 
 
@@ -73,6 +74,13 @@ def test_one_rank_per_gpu(world, scenario):
 @pytest.mark.parametrize("scenario", ["gather_scatter", "sampling"])
 def test_one_rank_per_gpu_forced_nccl_exchange(world, scenario):
     _run(world, scenario, env={"WG_FORCE_EXCHANGE": "1"})
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4])
+def test_one_rank_per_gpu_gradient_over_nccl(world):
+    """The all-to-all gradient exchange (used when GPUs cannot map each other) instead of the peer-store push."""
+    _run(world, "gradient", env={"WG_GRAD_PUSH": "0"})
 
 
 @pytest.mark.timeout(900)

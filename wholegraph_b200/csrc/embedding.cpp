@@ -4,8 +4,9 @@
  * :146-323, optimizer states :325-428, C API :900-1152) and embedding_optimizer.cpp (parameters
  * :65-75, defaults/state names :170-190, :307, :404-410) for the NON-CACHED embedding.
  *
- * Gradient path here:  bucket ids by owner -> exchange ids + fp32 gradient rows (exchange.cu;
- * skipped entirely on a 1-rank communicator) -> ONE fused merge+update kernel (sparse_optimizer.cu).
+ * Gradient path here:  bucket ids by owner -> (id, fp32 gradient row) pairs reach their owners by peer stores over
+ * NVLink (peer_push.cu; NCCL all-to-all in exchange.cu when the GPUs cannot map each other; nothing at all on a
+ * 1-rank communicator) -> ONE fused merge+update kernel (sparse_optimizer.cu).
  * The reference runs: bucket/sort, gather-permute, alltoallv, sort, unique_by_key, dedup kernel,
  * optimizer kernel.
  *
@@ -44,6 +45,7 @@ struct wholememory_embedding_ {
   wholememory_embedding_t state_embedding = nullptr; /* [N, state_stride] fp32, same type/location/partition */
   std::vector<std::pair<std::string, wholememory_tensor_t>> named_states;
   wholememory_tensor_t b12_padded = nullptr, b12_user = nullptr;
+  wm::push_stage grad_stage; /* peer-store gradient exchange (peer_push.cu), allocated on first use */
 };
 
 namespace wm {
@@ -190,8 +192,25 @@ wholememory_error_code_t gradient_apply(wholememory_embedding_t e,
   }
 
   auto* h = wholememory_tensor_get_memory_handle(e->allocated);
+  const auto first_rows = handle_first_rows(h, (size_t)adesc->strides[0] * sizeof(float));
   exchange_plan plan(env);
-  plan_exchange(&plan, comm, idx_ptr, idesc->dtype, n, handle_first_rows(h, (size_t)adesc->strides[0] * sizeof(float)), stream);
+  /* NVSwitch path: every rank stores its (id, gradient row) pairs straight into the owners' stages.  WG_GRAD_PUSH=0
+   * keeps the NCCL all-to-all below (also used when the ranks' GPUs cannot map each other). */
+  static const bool push_enabled = [] {
+    const char* v = getenv("WG_GRAD_PUSH");
+    return v == nullptr || v[0] != '0';
+  }();
+  if (push_enabled && comm->all_peer_capable && handle_is_addressable(h)) {
+    partition_by_owner(&plan, comm, idx_ptr, idesc->dtype, n, first_rows, stream);
+    const int64_t* recv_ids = nullptr;
+    const float* recv_rows  = nullptr;
+    int64_t n_recv = push_rows_to_owners(&e->grad_stage, comm, plan, grad_ptr, gdesc->strides[0], D, stream, &recv_ids, &recv_rows);
+    merge_and_update_rows(e->optimizer->type, recv_ids, WHOLEMEMORY_DT_INT64, n_recv, recv_rows, D, rows, e->optimizer->params, lr,
+                          total_rows, /*may_have_negative=*/false, env, stream);
+    /* asynchronous from here: the stage is double-buffered and the plan's temporaries were consumed before the barrier */
+    return WHOLEMEMORY_SUCCESS;
+  }
+  plan_exchange(&plan, comm, idx_ptr, idesc->dtype, n, first_rows, stream);
   temp_buffer outgoing(env), incoming(env);
   float* out_p = static_cast<float*>(outgoing.device((size_t)std::max<int64_t>(plan.n_send, 1) * D, WHOLEMEMORY_DT_FLOAT));
   float* in_p  = static_cast<float*>(incoming.device((size_t)std::max<int64_t>(plan.n_recv, 1) * D, WHOLEMEMORY_DT_FLOAT));
@@ -332,6 +351,7 @@ wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t e
   return wm::guarded("wholememory_destroy_embedding", [&]() -> wholememory_error_code_t {
     if (e == nullptr) return WHOLEMEMORY_INVALID_INPUT;
     wm::destroy_states(e);
+    wm::destroy_push_stage(&e->grad_stage);
     if (e->user) wholememory_destroy_tensor(e->user);
     if (e->allocated) WHOLEMEMORY_RETURN_ON_FAIL(wholememory_destroy_tensor(e->allocated));
     delete e;

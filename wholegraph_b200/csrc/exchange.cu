@@ -216,13 +216,13 @@ exchange_plan::exchange_plan(wholememory_env_func_t* env)
 {
 }
 
-void plan_exchange(exchange_plan* p,
-                   wholememory_comm_t comm,
-                   const void* indices,
-                   wholememory_dtype_t idx_dtype,
-                   int64_t n,
-                   const std::vector<int64_t>& first_row,
-                   cudaStream_t stream)
+void partition_by_owner(exchange_plan* p,
+                        wholememory_comm_t comm,
+                        const void* indices,
+                        wholememory_dtype_t idx_dtype,
+                        int64_t n,
+                        const std::vector<int64_t>& first_row,
+                        cudaStream_t stream)
 {
   const int ws = comm->world_size;
   WM_EXPECT(ws <= kMaxInlineRanks, WHOLEMEMORY_NOT_SUPPORTED, "bucket exchange supports at most %d ranks", kMaxInlineRanks);
@@ -270,6 +270,21 @@ void plan_exchange(exchange_plan* p,
     cudaEventDestroy(ev);
     for (int r = 0; r < ws; ++r) p->send_counts[r] = htot[r];
   }
+  p->n_send = 0;
+  for (int r = 0; r < ws; ++r) p->n_send += p->send_counts[r];
+}
+
+void plan_exchange(exchange_plan* p,
+                   wholememory_comm_t comm,
+                   const void* indices,
+                   wholememory_dtype_t idx_dtype,
+                   int64_t n,
+                   const std::vector<int64_t>& first_row,
+                   cudaStream_t stream)
+{
+  partition_by_owner(p, comm, indices, idx_dtype, n, first_row, stream);
+  const int ws     = comm->world_size;
+  const bool idx64 = idx_dtype == WHOLEMEMORY_DT_INT64;
   {
     std::lock_guard<std::mutex> lk(comm->mu);
     comm->boot->alltoall(p->send_counts.data(), p->recv_counts.data(), sizeof(int64_t));

@@ -17,7 +17,17 @@ struct exchange_plan {
   temp_buffer scratch_hist, scratch_base, scratch_totals, host_totals;
 };
 
-/* Collective.  first_row: world_size+1 partition boundaries in rows. */
+/* Local part of the plan: grouped_idx / origin / send_counts / n_send.  No communication.
+ * first_row: world_size+1 partition boundaries in rows. */
+void partition_by_owner(exchange_plan* p,
+                        wholememory_comm_t comm,
+                        const void* indices,
+                        wholememory_dtype_t idx_dtype,
+                        int64_t n,
+                        const std::vector<int64_t>& first_row,
+                        cudaStream_t stream);
+
+/* Collective: partition_by_owner + count all-to-all + shipping the grouped indices to their owners (NCCL). */
 void plan_exchange(exchange_plan* p,
                    wholememory_comm_t comm,
                    const void* indices,
@@ -37,5 +47,31 @@ void exchange_rows(const exchange_plan& p,
                    cudaStream_t stream);
 
 std::vector<int64_t> handle_first_rows(wholememory_handle_t h, size_t row_stride_bytes);
+
+/*
+ * Peer-store push of (row id, fp32 row) pairs to the owners' staging areas (peer_push.cu): the gradient exchange on an
+ * NVSwitch box.  The stage is a CHUNKED/DEVICE WholeMemory allocation every rank maps; it is double-buffered so that the
+ * owner's update kernel of step k may still run while step k+1's rows arrive.
+ */
+struct push_stage {
+  wholememory_handle_t h = nullptr;
+  int64_t cap_rows       = 0; /* rows per rank and buffer */
+  int64_t dim            = 0;
+  int flip               = 0;
+};
+
+/* Collective.  `p` must come from partition_by_owner.  On return every row addressed to this rank sits in its stage, in
+ * (sender rank, sender order) order - the order the NCCL exchange delivers - and is visible to `stream`:
+ * *ids = [n_recv] int64 global row ids, *rows = [n_recv, dim] fp32.  Returns n_recv. */
+int64_t push_rows_to_owners(push_stage* st,
+                            wholememory_comm_t comm,
+                            const exchange_plan& p,
+                            const float* rows_in,
+                            int64_t row_stride,
+                            int64_t dim,
+                            cudaStream_t stream,
+                            const int64_t** ids,
+                            const float** rows);
+void destroy_push_stage(push_stage* st);
 
 }  // namespace wm
