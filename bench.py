@@ -294,8 +294,13 @@ def main():
         t_hbm = alg_bytes / (hbm_peak * 1e9)
         t_nvl = n * row * (world - 1) / world / 770e9  # measured peer-copy bandwidth per direction (B200_PROFILING.md)
         bound_ms = max(t_hbm, t_nvl) * 1e3
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed `ncu --set full` capture
+        # (profiles/r1_gather_c2_full_summary.txt: same command, same kernel configuration); not re-measured in this run.
+        traffic, traffic_src = None, None
+        if args.impl != "reference" and world == 1 and (dim, esize, n) == (256, 4, 1 << 20):
+            traffic, traffic_src = 2.100e9, "profiles/r1_gather_c2_full_summary.txt (ncu --set full, 1.081 GB read + 1.020 GB written)"
         roof = {"bound": "hbm" if t_hbm >= t_nvl else "nvlink", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "wm::row_move_vec_kernel<int64,16B,gather>", "kernel_ms": round(ms_max, 4),
                 "bound_ms": round(bound_ms, 4), "frac_of_bound_time": round(bound_ms / ms_max, 4),
                 "algorithmic_bytes_per_launch": alg_bytes}

@@ -208,3 +208,47 @@ def test_gather_large_property_checks(env):
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
     G.wmb.destroy_wholememory_tensor(table)
+
+
+def test_scatter_and_gather_replay_from_a_cuda_graph(env):
+    """The mapped-memory ops allocate nothing and never touch the host after launch, so a training step can capture them
+    in a CUDA graph and replay it with new indices / rows in the same buffers (B200 launch-bound small-batch regime)."""
+    G = env
+    comm = G.single_comm()
+    rows, cols, n = 4096, 96, 1500
+    rng = np.random.default_rng(77)
+    table, view = G.create_table(comm, "chunked", "cuda", O.DT_FLOAT, rows, cols, cols)
+    base = G.random_table(rng, O.DT_FLOAT, rows, cols)
+    view.copy_(G.np_to_torch(base, O.DT_FLOAT))
+    src_t = torch.zeros(n, cols, device="cuda")
+    sidx_t = torch.zeros(n, dtype=torch.int64, device="cuda")
+    gidx_t = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out_t = torch.zeros(n, cols, dtype=torch.float16, device="cuda")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):  # warm-up outside capture (one-time lazy initialisation)
+        G.scatter(src_t, sidx_t, table)  # all-zero rows onto row 0; the table is restored below
+        G.gather(table, gidx_t, out_t)
+    side.synchronize()
+    view.copy_(G.np_to_torch(base, O.DT_FLOAT))
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        G.scatter(src_t, sidx_t, table)
+        G.gather(table, gidx_t, out_t)
+    exp_table = base.copy()
+    for trial in range(3):
+        sidx = rng.permutation(rows)[:n].astype(np.int64)
+        gidx = rng.integers(0, rows, size=n).astype(np.int32)
+        src = G.random_table(rng, O.DT_FLOAT, n, cols)
+        src_t.copy_(torch.from_numpy(src))
+        sidx_t.copy_(torch.from_numpy(sidx))
+        gidx_t.copy_(torch.from_numpy(gidx))
+        graph.replay()
+        torch.cuda.synchronize()
+        O.scatter(src, O.DT_FLOAT, sidx, exp_table, O.DT_FLOAT, cols=cols)
+        exp_out = np.zeros((n, cols), np.float16)
+        O.gather(exp_table, O.DT_FLOAT, gidx, O.DT_HALF, out=exp_out, cols=cols)
+        assert G.torch_to_np(view, O.DT_FLOAT).tobytes() == exp_table.tobytes(), f"table differs after replay {trial}"
+        assert G.torch_to_np(out_t, O.DT_HALF).tobytes() == exp_out.tobytes(), f"gathered rows differ after replay {trial}"
+    del graph
+    G.wmb.destroy_wholememory_tensor(table)

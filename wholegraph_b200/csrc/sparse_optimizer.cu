@@ -115,6 +115,17 @@ constexpr int kOptMinCtas = 8; /* <= 64 registers: 32 resident warps per SM */
  * tools/bench_ops.py, whole call): CTA per position 0.794 ms; warp per position U=4 (96 regs) 0.897, U=2 8-warp CTAs
  * 0.784, U=1 0.778; U=2 with 4-warp CTAs capped at 64 registers 0.710 <- this configuration.  The step has ~55
  * instructions per element (three IEEE divides and a square root), so resident warps matter more than loads per lane. */
+/* positions 0..n-1 plus a copy of the ids with every id outside [0, total_rows) replaced by total_rows */
+template <typename IdxT>
+__global__ void iota_fold_kernel(const IdxT* __restrict__ ids, IdxT* __restrict__ folded, int* __restrict__ pos, int n, IdxT total_rows)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const IdxT v = ids[i];
+  folded[i]    = (v < 0 || v >= total_rows) ? total_rows : v;
+  pos[i]       = i;
+}
+
 template <typename IdxT, int OPT, int VEC, int U>
 __global__ void __launch_bounds__(kOptWarps * 32, kOptMinCtas) fused_merge_update_kernel(const IdxT* __restrict__ sorted_idx,
                                                                             const int* __restrict__ sorted_pos,
@@ -237,19 +248,29 @@ void merge_update_typed(int opt, const void* idx, int64_t n, const float* grads,
   auto* sorted_idx = static_cast<IdxT*>(sorted_idx_b.device((size_t)n, idt));
   auto* pos_in     = static_cast<int*>(pos_in_b.device((size_t)n, WHOLEMEMORY_DT_INT));
   auto* pos_out    = static_cast<int*>(pos_out_b.device((size_t)n, WHOLEMEMORY_DT_INT));
-  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pos_in, (int)n);
-  /* ids are < total_rows (negatives keep their sign bit and sort first): only sort the bits in use */
-  /* non-negative ids below total_rows only need ceil(log2(total_rows)) bits: 3 onesweep passes instead of 8 for 5M rows.
-   * Negative ids (ignored by the kernel) would alias into that range, so they force the full width. */
+  /* Only the bits in use are sorted: ids below total_rows need ceil(log2(total_rows + 1)) bits, i.e. 3 onesweep passes
+   * instead of 8 for 5M rows.  Caller-supplied ids may be negative or out of range (ignored by the update kernel) and
+   * would alias into that range, so they are first folded onto ONE sentinel key, total_rows, in the pass that writes
+   * the positions anyway. */
+  const IdxT* keys_in = static_cast<const IdxT*>(idx);
+  temp_buffer folded_b(env);
   int end_bit = (int)sizeof(IdxT) * 8;
-  if (total_rows > 0 && !may_have_negative) {
+  const bool fits = total_rows > 0 && (sizeof(IdxT) == 8 || total_rows < (int64_t)0x7fffffff);
+  if (fits) {
     end_bit = 1;
-    while (end_bit < (int)sizeof(IdxT) * 8 && ((int64_t)1 << end_bit) < total_rows) ++end_bit;
+    while (end_bit < (int)sizeof(IdxT) * 8 && ((int64_t)1 << end_bit) <= total_rows) ++end_bit;
+  }
+  if (fits && may_have_negative) {
+    auto* folded = static_cast<IdxT*>(folded_b.device((size_t)n, idt));
+    iota_fold_kernel<IdxT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys_in, folded, pos_in, (int)n, (IdxT)total_rows);
+    keys_in = folded;
+  } else {
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pos_in, (int)n);
   }
   size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const IdxT*>(idx), sorted_idx, pos_in, pos_out, (int)n, 0, end_bit, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, sorted_idx, pos_in, pos_out, (int)n, 0, end_bit, s);
   void* cub_tmp = cub_b.device(cub_bytes, WHOLEMEMORY_DT_INT8);
-  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, static_cast<const IdxT*>(idx), sorted_idx, pos_in, pos_out, (int)n, 0, end_bit, s);
+  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, sorted_idx, pos_in, pos_out, (int)n, 0, end_bit, s);
   bool vec4 = rows.dim % 4 == 0 && grad_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0 &&
               rows.w_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(rows.w) & 15) == 0 &&
               (rows.state == nullptr || (rows.state_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(rows.state) & 15) == 0));
