@@ -1,0 +1,150 @@
+"""Native (C++) torch env functions -- wholegraph_b200/csrc/torch_ext/torch_env.cpp.
+
+CPU part: the module loads from the tree, exposes the reference extension's six entry points
+(pylibwholegraph/torch_cpp_ext/wholegraph_torch_ext.cpp:50-66), and its C callbacks follow the
+create_ctx -> malloc(desc, kind, ctx) -> free(ctx) -> destroy_ctx protocol of
+include/wholememory/env_func_ptrs.h for HOST allocations of every dtype.  GPU part: a sampling + gather +
+append_unique pass with the native table must give the same results as the Python-callback table."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from wholegraph_b200 import _lib
+from wholegraph_b200.torch import wholegraph_env as wenv
+
+
+@pytest.fixture()
+def native():
+    if not wenv.load_native_env():
+        pytest.skip("wholegraph_b200_torch_ext is not built")
+    yield wenv.torch_cpp_ext_lib
+    wenv.unload_native_env()
+
+
+def _env_table(addr):
+    return ctypes.cast(addr, ctypes.POINTER(_lib.EnvFns)).contents
+
+
+def _desc(shape, dtype):
+    d = _lib.TensorDescription()
+    for i, s in enumerate(shape):
+        d.sizes[i] = s
+    stride = 1
+    for i in reversed(range(len(shape))):
+        d.strides[i] = stride
+        stride *= shape[i]
+    d.dim = len(shape)
+    d.dtype = dtype
+    d.storage_offset = 0
+    return d
+
+
+def test_module_surface(native):
+    for name in ("get_wholegraph_env_fns", "get_stream", "create_output_context", "destroy_output_context",
+                 "free_context_data", "get_tensor_from_context"):
+        assert callable(getattr(native, name))
+    assert native.get_wholegraph_env_fns() != 0
+    assert native.get_wholegraph_env_fns() == wenv.get_wholegraph_env_fns()
+
+
+DTYPES = [(1, torch.float32), (2, torch.float16), (3, torch.float64), (4, torch.bfloat16), (5, torch.int32), (6, torch.int64),
+          (7, torch.int16), (8, torch.int8)]
+
+
+@pytest.mark.parametrize("wm_dtype,th_dtype", DTYPES)
+def test_temporary_protocol_host(native, wm_dtype, th_dtype):
+    env = _env_table(native.get_wholegraph_env_fns())
+    before = native.live_context_count()
+    ctx = ctypes.c_void_p()
+    env.temporary_fns.create_memory_context_fn(ctypes.byref(ctx), None)
+    assert ctx.value and native.live_context_count() == before + 1
+    d = _desc((5, 7), wm_dtype)
+    ptr = env.temporary_fns.malloc_fn(ctypes.byref(d), 2, ctx, None)  # WHOLEMEMORY_MA_HOST
+    assert ptr
+    t = native.get_tensor_from_context(ctx.value)
+    assert t.shape == (5, 7) and t.dtype == th_dtype and t.device.type == "cpu" and t.data_ptr() == ptr
+    ctypes.memset(ptr, 0, t.numel() * t.element_size())
+    assert int(t.to(torch.float64).abs().sum()) == 0
+    env.temporary_fns.free_fn(ctx, None)
+    assert native.get_tensor_from_context(ctx.value) is None
+    env.temporary_fns.destroy_memory_context_fn(ctx, None)
+    assert native.live_context_count() == before
+
+
+def test_output_context_lifecycle(native):
+    env = _env_table(native.get_wholegraph_env_fns())
+    before = native.live_context_count()
+    c = wenv.TorchMemoryContext()
+    assert c.get_c_context() == c.handle != 0
+    assert c.get_tensor() is None
+    d = _desc((11,), 6)
+    ptr = env.output_fns.malloc_fn(ctypes.byref(d), 2, c.get_c_context(), None)
+    np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int64)), shape=(11,))[:] = np.arange(11)
+    t = c.get_tensor()
+    assert t.tolist() == list(range(11))
+    c.free()
+    assert c.handle == 0 and native.live_context_count() == before
+    assert t.tolist() == list(range(11))  # the tensor outlives its context
+    # zero-size and bad requests
+    c = wenv.TorchMemoryContext()
+    d = _desc((0,), 5)
+    env.output_fns.malloc_fn(ctypes.byref(d), 2, c.get_c_context(), None)
+    assert c.get_tensor().numel() == 0
+    d = _desc((4,), 0)  # WHOLEMEMORY_DT_UNKNOWN
+    assert not env.output_fns.malloc_fn(ctypes.byref(d), 2, c.get_c_context(), None)
+    d = _desc((4,), 1)
+    assert not env.output_fns.malloc_fn(ctypes.byref(d), 0, c.get_c_context(), None)  # WHOLEMEMORY_MA_NONE
+    del c
+    assert native.live_context_count() == before
+
+
+def test_python_callbacks_unaffected_after_unload():
+    wenv.unload_native_env()
+    c = wenv.TorchMemoryContext()
+    assert c.get_c_context() == id(c)
+    c.free()
+
+
+@pytest.mark.gpu
+def test_native_env_matches_python_callbacks_on_gpu():
+    import gpu_utils as G
+    import wholegraph_b200.torch as wgth
+    from wholegraph_b200.torch.wholegraph_ops import unweighted_sample_without_replacement
+
+    comm = wgth.WholeMemoryCommunicator(G.single_comm())
+    rng = np.random.default_rng(3)
+    nodes = 3000
+    deg = rng.integers(0, 60, size=nodes)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, nodes, size=int(row_ptr[-1])).astype(np.int64)
+    rp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [nodes + 1], torch.int64, [1])
+    cp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [col.size], torch.int64, [1])
+    rp.get_local_tensor()[0].copy_(torch.from_numpy(row_ptr))
+    cp.get_local_tensor()[0].copy_(torch.from_numpy(col))
+    centers = torch.from_numpy(rng.integers(0, nodes, size=2048).astype(np.int64)).cuda()
+    targets = torch.from_numpy(rng.permutation(nodes)[:500].astype(np.int64)).cuda()
+
+    def one_pass():
+        res = unweighted_sample_without_replacement(rp.wmb_tensor, cp.wmb_tensor, centers, 25, random_seed=99,
+                                                    need_center_local_output=True, need_edge_output=True)
+        uniq, mapping = wgth.append_unique(targets, res[1], need_neighbor_raw_to_unique=True)
+        torch.cuda.synchronize()
+        return [r.cpu() for r in res] + [uniq.cpu(), mapping.cpu()]
+
+    wenv.unload_native_env()
+    expect = one_pass()
+    assert wenv.load_native_env(required=True)
+    try:
+        lib = wenv.torch_cpp_ext_lib
+        before = lib.live_context_count()
+        assert lib.get_stream() == wenv.get_stream()
+        for _ in range(3):
+            got = one_pass()
+            assert len(got) == len(expect) and all(torch.equal(a, b) for a, b in zip(got, expect))
+        assert lib.live_context_count() == before
+    finally:
+        wenv.unload_native_env()
+        wgth.destroy_wholememory_tensor(rp)
+        wgth.destroy_wholememory_tensor(cp)

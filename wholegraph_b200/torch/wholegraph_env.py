@@ -5,6 +5,9 @@ allocator, outputs are returned to the caller as tensors.  The callbacks are cty
 the same four-function protocol as the reference (create_ctx / malloc / free / destroy_ctx).
 """
 import ctypes
+import glob
+import importlib.util
+import os
 from typing import Union
 
 import torch
@@ -14,6 +17,48 @@ from .. import binding as wmb
 from .utils import torch_dtype_to_wholememory_dtype, wholememory_dtype_to_torch_dtype
 
 default_wholegraph_env_context = None
+_parked = []
+
+# Native (C++) env functions: wholegraph_b200/csrc/torch_ext/torch_env.cpp, built in-tree into wholegraph_b200/lib/.
+# With them an op call never re-enters the interpreter for its allocations (reference: the optional torch_cpp_ext,
+# pylibwholegraph/torch/wholegraph_env.py:183-231).  Opt-in with WG_TORCH_NATIVE_ENV=1 until verified on the GPU box.
+torch_cpp_ext_loaded = False
+torch_cpp_ext_lib = None
+
+
+def load_native_env(required: bool = False) -> bool:
+    """Load the in-tree native env-function module; returns whether it is active."""
+    global torch_cpp_ext_loaded, torch_cpp_ext_lib, default_wholegraph_env_context
+    if torch_cpp_ext_loaded:
+        return True
+    lib_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib")
+    found = sorted(glob.glob(os.path.join(lib_dir, "wholegraph_b200_torch_ext*.so")))
+    if not found:
+        if required:
+            raise ImportError("wholegraph_b200_torch_ext is not built (run __graft_entry__.build())")
+        return False
+    spec = importlib.util.spec_from_file_location("wholegraph_b200_torch_ext", found[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch_cpp_ext_lib = mod
+    torch_cpp_ext_loaded = True
+    _retire_default_context()  # rebuilt on next use with the native table
+    return True
+
+
+def unload_native_env():
+    """Back to the Python-callback env functions (the module stays imported)."""
+    global torch_cpp_ext_loaded
+    torch_cpp_ext_loaded = False
+    _retire_default_context()
+
+
+def _retire_default_context():
+    """Stop handing out the current default table but keep it alive: callers may still hold its address."""
+    global default_wholegraph_env_context
+    if default_wholegraph_env_context is not None:
+        _parked.append(default_wholegraph_env_context)
+    default_wholegraph_env_context = None
 
 
 def get_stream():
@@ -25,28 +70,46 @@ class TorchMemoryContext(object):
     """Owns one torch tensor allocated on behalf of the library."""
     _live = {}
 
-    def __init__(self):
+    def __init__(self, native=None):
         self.tensor = None
-        TorchMemoryContext._live[id(self)] = self
+        self.handle = 0
+        if torch_cpp_ext_loaded if native is None else native:
+            self._ext = torch_cpp_ext_lib
+            self.handle = self._ext.create_output_context()
+        else:
+            self._ext = None
+            TorchMemoryContext._live[id(self)] = self
 
     def get_c_context(self):
-        return id(self)
+        return self.handle if self._ext is not None else id(self)
 
     def set_tensor(self, t):
         self.tensor = t
 
     def get_tensor(self):
+        if self._ext is not None and self.handle != 0:
+            self.tensor = self._ext.get_tensor_from_context(self.handle)
         return self.tensor
 
     def free_data(self):
         self.tensor = None
+        if self._ext is not None and self.handle != 0:
+            self._ext.free_context_data(self.handle)
 
     def free(self):
         self.tensor = None
-        TorchMemoryContext._live.pop(id(self), None)
+        if self._ext is not None:
+            if self.handle != 0:
+                self._ext.destroy_output_context(self.handle)
+                self.handle = 0
+        else:
+            TorchMemoryContext._live.pop(id(self), None)
 
     def __del__(self):
-        TorchMemoryContext._live.pop(id(self), None)
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def _ctx(handle):
@@ -77,7 +140,7 @@ _temp_contexts = {}
 
 
 def _torch_create_ctx(out_ctx, global_context):
-    ctx = TorchMemoryContext()
+    ctx = TorchMemoryContext(native=False)
     _temp_contexts[id(ctx)] = ctx  # library-owned until destroy
     out_ctx[0] = id(ctx)
 
@@ -111,7 +174,19 @@ class GlobalContextWrapper(object):
         return ctypes.addressof(self.env)
 
 
+class ExtContextWrapper(object):
+    """The native module's static wholememory_env_func_t table."""
+
+    def __init__(self, env_func: int):
+        self.env_func = env_func
+
+    def get_env_fns(self) -> int:
+        return self.env_func
+
+
 def create_current_env_context():
+    if torch_cpp_ext_loaded:
+        return ExtContextWrapper(torch_cpp_ext_lib.get_wholegraph_env_fns())
     return GlobalContextWrapper()
 
 
@@ -128,9 +203,6 @@ def get_wholegraph_env_fns(use_default=True) -> int:
     return default_wholegraph_env_context.get_env_fns()
 
 
-_parked = []
-
-
 def wrap_torch_tensor(t: Union[torch.Tensor, None]) -> wmb.WrappedLocalTensor:
     py_desc = wmb.PyWholeMemoryTensorDescription()
     wm_t = wmb.WrappedLocalTensor()
@@ -143,3 +215,7 @@ def wrap_torch_tensor(t: Union[torch.Tensor, None]) -> wmb.WrappedLocalTensor:
     w = wm_t.wrap_tensor(py_desc, t.data_ptr())
     w._keepalive = t
     return w
+
+
+if os.environ.get("WG_TORCH_NATIVE_ENV", "0") == "1":
+    load_native_env(required=True)
