@@ -4,15 +4,19 @@
 # oracle and the "reference arm" of bench.py.  No reference source is copied into the repo; only objects and the
 # .so are written, under the git-ignored oracle/_ref/.  The reference's cmake build needs network (rapids-cmake,
 # RAFT via CPM), so the few translation units on the path are compiled directly with a ~70-line RAFT shim
-# (oracle/ref_shim) -- recipe from SURVEY.md Appendix B.  Embedding/optimizer/sampling TUs need real RAFT headers
-# and are NOT built.
+# (oracle/ref_shim) -- recipe from SURVEY.md Appendix B.  The sparse-optimizer kernels
+# (functions/embedding_optimizer_func.cu) are built too: that TU includes the embedding-cache header only for
+# `CacheLineInfo`, and a declaration-only stand-in for RAFT's warp top-k queue
+# (ref_shim/raft/matrix/detail/select_k-inl.cuh) lets it compile; ref_optimizer_hook.cpp exposes
+# dedup + optimizer step as one extern "C" test entry.  Embedding/cache/sampling TUs need real RAFT and are NOT built.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF_ROOT:-/root/reference}"
 OUT="$HERE/_ref"
 OBJ="$OUT/obj"
 [ -d "$REF/cpp/src" ] || { echo "no reference tree at $REF"; exit 3; }
-if [ -f "$OUT/libwholegraph_ref.so" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_stubs.cpp" ]; then
+if [ -f "$OUT/libwholegraph_ref.so" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_stubs.cpp" ] \
+   && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_optimizer_hook.cpp" ]; then
   echo "oracle/_ref/libwholegraph_ref.so is up to date"; exit 0
 fi
 mkdir -p "$OBJ"
@@ -31,6 +35,7 @@ CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl
  wholememory_ops/functions/gather_func.cu wholememory_ops/functions/scatter_func.cu
  wholememory_ops/functions/bucket_ids_func.cu wholememory_ops/functions/exchange_ids_nccl_func.cu
  wholememory_ops/functions/exchange_embeddings_nccl_func.cu wholememory_ops/functions/sort_indices_func.cu
+ wholememory_ops/functions/embedding_optimizer_func.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int32_indices.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int64_indices.cu
  wholememory_ops/functions/gather_func_impl_integer_data_int32_indices.cu
@@ -46,6 +51,7 @@ MK="$OBJ/Makefile"
   for f in $CPP; do o="$OBJ/$(echo "$f" | tr '/' '_').o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$S/$f" "$CXXFLAGS"; done
   for f in $CU; do o="$OBJ/$(echo "$f" | tr '/' '_').o"; OBJS="$OBJS $o"; printf '%s: %s\n\t%s %s -c $< -o $@\n' "$o" "$S/$f" "$NVCC" "$NVFLAGS"; done
   o="$OBJ/ref_stubs.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_stubs.cpp" "$CXXFLAGS"
+  o="$OBJ/ref_optimizer_hook.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_optimizer_hook.cpp" "$CXXFLAGS"
   echo "objs:$OBJS"
   echo "OBJS=$OBJS"
 } > "$MK"
