@@ -8,7 +8,8 @@
 # (functions/embedding_optimizer_func.cu) are built too: that TU includes the embedding-cache header only for
 # `CacheLineInfo`, and a declaration-only stand-in for RAFT's warp top-k queue
 # (ref_shim/raft/matrix/detail/select_k-inl.cuh) lets it compile; ref_optimizer_hook.cpp exposes
-# dedup + optimizer step as one extern "C" test entry.  Embedding/cache/sampling TUs need real RAFT and are NOT built.
+# dedup + optimizer step as one extern "C" test entry.  graph_ops/ (append_unique, csr_add_self_loop) needs only
+# integer_utils and is built as is.  Embedding/cache/sampling TUs need real RAFT and are NOT built.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF_ROOT:-/root/reference}"
@@ -29,13 +30,15 @@ CPP="cuda_macros.cpp logger.cpp
  wholememory/communicator.cpp wholememory/nccl_comms.cpp wholememory/memory_handle.cpp wholememory/wholememory.cpp
  wholememory/wholememory_tensor.cpp wholememory/tensor_description.cpp wholememory/env_func_ptrs.cpp
  wholememory/initialize.cpp wholememory/system_info.cpp wholememory/global_reference.cpp
- wholememory_ops/gather_op.cpp wholememory_ops/scatter_op.cpp wholememory_ops/thrust_allocator.cpp"
+ wholememory_ops/gather_op.cpp wholememory_ops/scatter_op.cpp wholememory_ops/thrust_allocator.cpp
+ graph_ops/append_unique.cpp graph_ops/csr_add_self_loop.cpp"
 CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl.cu
  wholememory_ops/scatter_op_impl_mapped.cu wholememory_ops/scatter_op_impl_nccl.cu
  wholememory_ops/functions/gather_func.cu wholememory_ops/functions/scatter_func.cu
  wholememory_ops/functions/bucket_ids_func.cu wholememory_ops/functions/exchange_ids_nccl_func.cu
  wholememory_ops/functions/exchange_embeddings_nccl_func.cu wholememory_ops/functions/sort_indices_func.cu
  wholememory_ops/functions/embedding_optimizer_func.cu
+ graph_ops/append_unique_impl.cu graph_ops/csr_add_self_loop_impl.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int32_indices.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int64_indices.cu
  wholememory_ops/functions/gather_func_impl_integer_data_int32_indices.cu
