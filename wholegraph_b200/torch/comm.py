@@ -23,10 +23,11 @@ all_comm_local_size = 1
 
 def reset_communicators():
     global all_comm_world_rank, all_comm_world_size, all_comm_local_rank, all_comm_local_size
-    global global_communicators, local_node_communicator, local_device_communicator
+    global global_communicators, local_node_communicator, local_device_communicator, local_mnnvl_communicator
     global_communicators = {}
     local_node_communicator = None
     local_device_communicator = None
+    local_mnnvl_communicator = None
     all_comm_world_rank = 0
     all_comm_world_size = 1
     all_comm_local_rank = 0
@@ -170,3 +171,20 @@ def get_local_device_communicator():
             assert "nccl" not in global_communicators
             global_communicators["nccl"] = local_device_communicator
     return local_device_communicator
+
+
+local_mnnvl_communicator = None
+
+
+def get_local_mnnvl_communicator():
+    """Communicator over the ranks of this GPU's multi-node-NVLink clique (reference comm.py:257-279).  A single
+    NVSwitch box reports no clique (wholememory_communicator_get_clique_info: is_in_clique = 0), so this raises the
+    same RuntimeError as the reference does on non-MNNVL hardware."""
+    global local_mnnvl_communicator
+    if local_mnnvl_communicator is None:
+        g_communicator = get_global_communicator()
+        is_in_clique, _, _, _, clique_id, _ = g_communicator.get_clique_info()
+        if not is_in_clique:
+            raise RuntimeError("the gpu does not belong to any mnnvl domain,can not create local_mnnvl_communicator")
+        local_mnnvl_communicator = split_communicator(g_communicator, clique_id)
+    return local_mnnvl_communicator

@@ -9,9 +9,10 @@ from typing import List, Union
 import torch
 
 from .. import binding as wmb
-from .comm import WholeMemoryCommunicator, get_global_communicator
+from .comm import (WholeMemoryCommunicator, get_global_communicator, get_local_device_communicator,
+                   get_local_node_communicator)
 from .tensor import WholeMemoryTensor
-from .utils import (str_to_wmb_wholememory_access_type, str_to_wmb_wholememory_location,
+from .utils import (get_file_size, str_to_wmb_wholememory_access_type, str_to_wmb_wholememory_location,
                     str_to_wmb_wholememory_memory_type, str_to_wmb_wholememory_optimizer_type,
                     torch_dtype_to_wholememory_dtype)
 from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
@@ -60,6 +61,41 @@ def create_wholememory_cache_policy(cache_comm: WholeMemoryCommunicator, *, memo
 def destroy_wholememory_cache_policy(cache_policy: WholeMemoryCachePolicy):
     cache_policy.wmb_cache_policy.destroy_policy()
     cache_policy.wmb_cache_policy = None
+
+
+_BUILTIN_CACHE_COMM = {"all_devices": get_global_communicator, "local_node": get_local_node_communicator,
+                       "local_device": get_local_device_communicator}
+
+
+def create_builtin_cache_policy(builtin_cache_type: str, embedding_memory_type: str, embedding_memory_location: str,
+                                access_type: str, cache_ratio: float, *, cache_memory_type: str = "",
+                                cache_memory_location: str = ""):
+    """Named cache layouts of the reference (pylibwholegraph/torch/embedding.py:122-211): "none" -> None; "all_devices",
+    "local_node", "local_device" pick the communicator the cache is sharded over and the cache's memory type
+    (embedding's type / chunked / continuous unless given).  Same argument checks and defaults; note that creating an
+    embedding WITH a cache policy is refused by this build (the cache hides host-memory latency, tables here live in HBM)."""
+    if embedding_memory_type not in ("continuous", "chunked", "distributed", "hierarchy"):
+        raise ValueError(f"embedding_memory_type={embedding_memory_type} is not valid")
+    if embedding_memory_location not in ("cpu", "cuda"):
+        raise ValueError(f"embedding_memory_location={embedding_memory_location} is not valid")
+    if builtin_cache_type == "none":
+        return None
+    if cache_memory_location not in ("", "cpu", "cuda"):
+        raise ValueError(f"cache_memory_location is {cache_memory_location}, should be empty or cpu, cuda")
+    if builtin_cache_type not in _BUILTIN_CACHE_COMM:
+        raise ValueError(f"builtin_cache_type={builtin_cache_type} not supported, "
+                         f"should be none, local_device, local_node or all_devices")
+    if builtin_cache_type == "all_devices":
+        if embedding_memory_location == "cuda":
+            print("[WARNING] a device cache in front of device memory costs memory and is slower than no cache")
+        memory_type = cache_memory_type or embedding_memory_type
+    elif builtin_cache_type == "local_node":
+        memory_type = cache_memory_type or "chunked"
+    else:
+        memory_type = "continuous"
+    return create_wholememory_cache_policy(_BUILTIN_CACHE_COMM[builtin_cache_type](), memory_type=memory_type,
+                                           memory_location=cache_memory_location or "cuda", access_type=access_type,
+                                           ratio=cache_ratio)
 
 
 class EmbeddingLookupFn(torch.autograd.Function):
@@ -199,6 +235,30 @@ def create_embedding(comm: WholeMemoryCommunicator, memory_type: str, memory_loc
         local_tensor, local_offset = wm_embedding.get_embedding_tensor().get_local_tensor()
         torch.nn.init.xavier_uniform_(local_tensor)
     comm.barrier()
+    return wm_embedding
+
+
+def create_embedding_from_filelist(comm: WholeMemoryCommunicator, memory_type: str, memory_location: str,
+                                   filelist: Union[List[str], str], dtype: torch.dtype, last_dim_size: int, *,
+                                   cache_policy: Union[WholeMemoryCachePolicy, None] = None,
+                                   embedding_entry_partition: Union[List[int], None] = None, gather_sms: int = -1,
+                                   round_robin_size: int = 0):
+    """Create an embedding sized from, and filled with, raw row-major binary files of [rows, last_dim_size] `dtype`
+    (reference: pylibwholegraph/torch/embedding.py:462-524)."""
+    if isinstance(filelist, str):
+        filelist = [filelist]
+    assert last_dim_size > 0
+    row_bytes = torch.tensor([], dtype=dtype).element_size() * last_dim_size
+    total_bytes = 0
+    for filename in filelist:
+        file_size = get_file_size(filename)
+        if file_size % row_bytes != 0:
+            raise ValueError("File %s size is %d not mutlple of %d" % (filename, file_size, row_bytes))
+        total_bytes += file_size
+    wm_embedding = create_embedding(comm, memory_type, memory_location, dtype, [total_bytes // row_bytes, last_dim_size],
+                                    cache_policy=cache_policy, embedding_entry_partition=embedding_entry_partition,
+                                    gather_sms=gather_sms, round_robin_size=round_robin_size)
+    wm_embedding.get_embedding_tensor().from_filelist(filelist, round_robin_size)
     return wm_embedding
 
 

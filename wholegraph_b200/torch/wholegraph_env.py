@@ -46,6 +46,16 @@ def load_native_env(required: bool = False) -> bool:
     return True
 
 
+def compile_cpp_extension():
+    """Build (if needed) and activate the native env functions -- the reference's entry point of the same name
+    (pylibwholegraph/torch/wholegraph_env.py:189-231) JIT-compiles its torch_cpp_ext; here the module is built
+    in-tree by wholegraph_b200/csrc/torch_ext/build.sh."""
+    import subprocess
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "torch_ext", "build.sh")
+    subprocess.check_call(["bash", script])
+    load_native_env(required=True)
+
+
 def unload_native_env():
     """Back to the Python-callback env functions (the module stays imported)."""
     global torch_cpp_ext_loaded
