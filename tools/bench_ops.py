@@ -76,6 +76,38 @@ def main():
                         "ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
         wgth.destroy_wholememory_optimizer(opt)
         wgth.destroy_embedding(emb)
+    if "refadam" in args.what:
+        # The REFERENCE's own dedup + LazyAdam kernels (oracle/_ref build, oracle/ref_optimizer_hook.cpp) on the workload of the
+        # "adam" entry above.  Run with WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so python tools/bench_ops.py --what refadam
+        # The hook cudaMallocs its two dedup buffers and synchronises the stream per call (the reference pipeline also
+        # synchronises, embedding.cpp:146-323); both are inside the timed region, as the sort is inside ours.
+        import ctypes
+        from wholegraph_b200 import _lib
+        fn = _lib.lib.wgref_dedup_and_optimizer_step
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [ctypes.c_int] + \
+                      [ctypes.c_float] * 2 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+        rows, dim, n = args.rows // 4, 512, 1 << 18
+        w = torch.randn(rows, dim, device="cuda")
+        state = torch.zeros(rows, 2 * dim, device="cuda")
+        b12 = torch.ones(rows, 2, device="cuda")
+        grads = torch.randn(n, dim, device="cuda")
+        w_w, w_s, w_b, w_g = (wrap_torch_tensor(t) for t in (w, state, b12, grads))
+        for name, idx in (("uniform", torch.randint(0, rows, (n,), device="cuda", generator=g)),
+                          ("unique", torch.randperm(rows, device="cuda", generator=g)[:n].contiguous())):
+            w_i = wrap_torch_tensor(idx)
+            uniq = int(torch.unique(idx).numel())
+            dd = ctypes.c_int64(0)
+
+            def f():
+                rc = fn(2, w_i.get_c_handle(), w_g.get_c_handle(), w_w.get_c_handle(), w_s.get_c_handle(), w_b.get_c_handle(), 0,
+                        0.0, 1e-8, 0.9, 0.999, 0, 0.99, 0.01, env, get_stream(), ctypes.byref(dd))
+                assert rc == 0
+            ms = timeit(f, steps=10, warmup=3)
+            assert dd.value == uniq
+            alg = n * dim * 4 + uniq * (6 * dim * 4 + 16) + n * 8
+            out.append({"op": "REFERENCE dedup + LazyAdam kernels %dx%d, %d grads (%s, %d unique), hook call" % (rows, dim, n, name, uniq),
+                        "ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
     if "sample" in args.what:
         nodes = 10_000_000
         deg = torch.clamp((torch.rand(nodes, device="cuda", generator=g) ** -0.7).long(), max=10000)
