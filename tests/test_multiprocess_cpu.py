@@ -79,3 +79,50 @@ def test_control_plane_world_size_n_over_gloo(world_size):
             p.kill()
             pytest.fail("rank hung")
     assert dict(results) == {r: "ok" for r in range(world_size)}, dict(results)
+
+
+def _timeout_worker(rank, world_size, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["WG_BOOTSTRAP_TIMEOUT_S"] = "2"
+    import time
+    import wholegraph_b200.torch as wgth
+    try:
+        wgth.init_torch_env(rank, world_size, rank, world_size, wm_log_level="warn", backend="gloo")
+        comm = wgth.get_global_communicator()
+        comm.barrier()  # everybody: fine
+        if rank == 0:
+            t0 = time.time()
+            try:
+                comm.barrier()  # rank 1 never joins this one
+                results[rank] = "FAIL: barrier returned"
+            except RuntimeError as e:
+                dt = time.time() - t0
+                results[rank] = "ok" if 1.0 < dt < 30.0 else "FAIL: gave up after %.1f s (%s)" % (dt, e)
+        else:
+            time.sleep(8)  # alive, socket open, but on a different code path
+            results[rank] = "ok"
+    except Exception:  # pragma: no cover
+        import traceback
+        results[rank] = "FAIL: " + traceback.format_exc()
+
+
+@pytest.mark.timeout(120)
+def test_collective_mismatch_ends_in_an_error_not_a_hang():
+    """A rank that waits for a collective its peer never issues must get WHOLEMEMORY_COMMUNICATION_ERROR after
+    WG_BOOTSTRAP_TIMEOUT_S, not block forever (a hung GPU box costs a whole run)."""
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(90)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("rank hung")
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)

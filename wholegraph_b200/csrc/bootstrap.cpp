@@ -9,8 +9,10 @@
  */
 #include "wm_internal.hpp"
 
+#include <algorithm>
 #include <errno.h>
 #include <fcntl.h>
+#include <stdlib.h>
 #include <poll.h>
 #include <sys/socket.h>
 #include <sys/un.h>
@@ -22,6 +24,36 @@ namespace wm {
 namespace {
 
 constexpr int kConnectTimeoutMs = 120000;
+
+/* A collective whose peer never answers (a rank that died without closing its socket cannot happen on one box, but a
+ * rank that took a different code path can) must end in an error, not in a hang: every blocking receive gives up after
+ * WG_BOOTSTRAP_TIMEOUT_S seconds (default 1800; 0 = wait forever). */
+int recv_timeout_ms()
+{
+  static const int ms = [] {
+    const char* v = getenv("WG_BOOTSTRAP_TIMEOUT_S");
+    long s        = (v && *v) ? atol(v) : 1800;
+    if (s <= 0) return -1;
+    return (int)std::min<long>(s, 2000000) * 1000;
+  }();
+  return ms;
+}
+
+/* waits until fd is readable; throws on timeout */
+void wait_readable(int fd)
+{
+  const int limit = recv_timeout_ms();
+  for (;;) {
+    pollfd pfd{fd, POLLIN, 0};
+    int r = ::poll(&pfd, 1, limit);
+    if (r > 0) return;
+    if (r < 0 && errno == EINTR) continue;
+    if (r == 0)
+      WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap: no answer from a peer rank within %d s (ranks issued different collectives?)",
+               limit / 1000);
+    WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap poll failed: %s", strerror(errno));
+  }
+}
 
 socklen_t make_addr(const wholememory_unique_id_t& uid, sockaddr_un* addr)
 {
@@ -61,6 +93,7 @@ void bootstrap::recv_all(int fd, void* p, size_t n)
 {
   char* c = static_cast<char*>(p);
   while (n > 0) {
+    wait_readable(fd);
     ssize_t r = ::recv(fd, c, n, 0);
     if (r < 0) {
       if (errno == EINTR) continue;
@@ -113,6 +146,7 @@ int bootstrap::recv_fd(int sock)
   msg.msg_control    = ctrl;
   msg.msg_controllen = sizeof(ctrl);
   for (;;) {
+    wait_readable(sock);
     ssize_t r = ::recvmsg(sock, &msg, MSG_CMSG_CLOEXEC);
     if (r < 0 && errno == EINTR) continue;
     if (r != 1) WM_THROW(WHOLEMEMORY_COMMUNICATION_ERROR, "bootstrap recvmsg(fd) failed: %s", strerror(errno));
