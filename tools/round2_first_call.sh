@@ -1,0 +1,45 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~25 min): everything that was written after round 1's GPU budget ran out gets
+# its first execution, then the headline numbers and ncu evidence are refreshed under r2 names.
+#   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+R=${ROUND_TAG:-r2}
+step() { echo "=== $*"; }
+
+step "1. full GPU suite (incl. tests/test_zz_*: native env, reference-binary optimizer + graph-ops parity, full-size configs)"
+timeout 1500 python -X faulthandler -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$R.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_$R.log | cut -c1-300
+# if -x stopped early, still learn what the new files do on their own
+for f in tests/test_zz_native_env.py tests/test_zz_ref_optimizer_parity_gpu.py tests/test_zz_ref_graph_ops_parity_gpu.py tests/test_zz_baseline_configs_gpu.py; do
+  timeout 900 python -X faulthandler -m pytest $f -m gpu -q -s > gpurun_out/$(basename $f .py)_$R.log 2>&1; echo "$f rc=$?"; grep -E "bit-identical|passed|failed|Error" gpurun_out/$(basename $f .py)_$R.log | tail -6 | cut -c1-300
+done
+
+step "2. smoke + both bench arms"
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --impl reference > gpurun_out/bench_reference_$R.json 2> gpurun_out/bench_reference_$R.err; tail -1 gpurun_out/bench_reference_$R.json | cut -c1-400
+timeout 900 python bench.py > gpurun_out/bench_ours_$R.json 2> gpurun_out/bench_ours_$R.err; tail -1 gpurun_out/bench_ours_$R.json | cut -c1-1800
+
+step "3. ncu: launch list of the bench command + one full capture of the gather kernel"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_bench_c2.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:row_move_vec -s 4 -c 1 -o gpurun_out/${R}_gather_c2_full -f python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --rows-per-gpu 20000000 > gpurun_out/ncu_gather_$R.log 2>&1
+ncu -i gpurun_out/${R}_gather_c2_full.ncu-rep --page raw --csv 2>/dev/null | python - <<'PY' > gpurun_out/${R}_gather_c2_full_summary.txt
+import csv, sys
+rows = list(csv.reader(sys.stdin))
+if len(rows) >= 3:
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    want = ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
+            "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct")
+    for h, u, v in zip(hdr, units, vals):
+        if h in want:
+            print("%-60s %s %s" % (h, v, u))
+PY
+cat gpurun_out/${R}_gather_c2_full_summary.txt
+
+step "4. other kernels, the reference's optimizer kernels next to ours, native env A/B on the sampler"
+timeout 600 python tools/bench_ops.py 2>&1 | tail -8
+WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 600 python tools/bench_ops.py --what refadam 2>&1 | tail -3
+WG_TORCH_NATIVE_ENV=1 timeout 600 python tools/bench_ops.py --what sample 2>&1 | tail -4
+timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
+WG_TORCH_NATIVE_ENV=1 timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
+ls -la gpurun_out | tail -12
