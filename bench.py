@@ -292,7 +292,38 @@ def main():
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         assert torch.equal(out_host[:, 0], (idx_host[(e_steps - 1) % 2] & mask).to(th_dtype))
         e2e = {"value": round(n * dim * esize * world / (float(e_ms.item()) * 1e-3) / 1e9, 3), "unit": "GB/s",
-               "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * dim * esize, "ms_per_step": round(float(e_ms.item()), 4)}
+               "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * dim * esize, "ms_per_step": round(float(e_ms.item()), 4),
+               "note": "PCIe-bound: the %d MB of gathered rows cross PCIe to pinned host memory every step" % (n * dim * esize >> 20)}
+        # Informational only (NOT the e2e figure): the way the library is used by a GNN loader -- indices arrive from pinned
+        # host memory, the gathered rows stay in HBM for the model, and 8 bytes (a checksum of the step's rows) return.
+        try:
+            if world > 1:
+                raise RuntimeError("single-GPU leg only (a rank-local failure must not strand the others in a collective)")
+            chk_host = torch.empty(1, dtype=torch.float64).pin_memory()
+
+            def resident_step(i):
+                idx_stage.copy_(idx_host[i % 2], non_blocking=True)
+                wmb.wholememory_gather_op(table, w_stage, w_out, env, sptr)
+                chk_host.copy_(out[:, 0].sum(dtype=torch.float64).reshape(1), non_blocking=True)
+
+            resident_step(0)
+            sync_all()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for i in range(e_steps):
+                resident_step(i)
+            r1.record(stream)
+            sync_all()
+            r_ms = torch.tensor([r0.elapsed_time(r1) / e_steps], device="cuda", dtype=torch.float64)
+            exp_chk = float((idx_host[(e_steps - 1) % 2] & mask).to(torch.float64).sum())
+            if abs(float(chk_host.item()) - exp_chk) <= 1e-6 * max(1.0, abs(exp_chk)):
+                e2e["device_resident_output"] = {"value": round(n * dim * esize * world / (float(r_ms.item()) * 1e-3) / 1e9, 3), "unit": "GB/s",
+                                                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": 8,
+                                                 "ms_per_step": round(float(r_ms.item()), 4),
+                                                 "note": "informational: rows stay in HBM, an 8-byte checksum returns"}
+        except Exception as ex:  # never let the informational leg break the bench line
+            if world == 1:
+                print("device-resident e2e leg skipped: %r" % (ex,), file=sys.stderr)
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
