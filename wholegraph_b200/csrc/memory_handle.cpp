@@ -127,11 +127,29 @@ void vmm_create(wholememory_handle_t h, bool map_peers)
   prop.location.type        = CU_MEM_LOCATION_TYPE_DEVICE;
   prop.location.id          = c->dev_id;
   prop.requestedHandleTypes = share ? CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR : CU_MEM_HANDLE_TYPE_NONE;
+  CUresult created = CUDA_SUCCESS;
   if (h->map_sizes[me] > 0) {
-    CUresult r = d.MemCreate(&h->phys[me], h->map_sizes[me], &prop, 0);
-    if (r == CUDA_ERROR_OUT_OF_MEMORY)
-      WM_THROW(WHOLEMEMORY_OUT_OF_MEMORY, "cuMemCreate(%zu bytes) out of device memory", h->map_sizes[me]);
-    WM_CU(r);
+    created = d.MemCreate(&h->phys[me], h->map_sizes[me], &prop, 0);
+    if (created != CUDA_SUCCESS) h->phys[me] = 0;
+  }
+  /* An allocation failure has to be collective: a rank that left here alone would strand the others in the fd
+   * exchange below.  Everybody learns everybody's result and all ranks fail together. */
+  int failed_rank = created != CUDA_SUCCESS ? me : -1;
+  if (ws > 1) {
+    int32_t mine = (int32_t)created;
+    std::vector<int32_t> all(ws, 0);
+    c->boot->allgather(&mine, all.data(), sizeof(mine));
+    for (int r = 0; r < ws && failed_rank < 0; ++r)
+      if (all[r] != (int32_t)CUDA_SUCCESS) {
+        failed_rank = r;
+        created     = (CUresult)all[r];
+      }
+  }
+  if (failed_rank >= 0) {
+    if (created == CUDA_ERROR_OUT_OF_MEMORY)
+      WM_THROW(WHOLEMEMORY_OUT_OF_MEMORY, "cuMemCreate(%zu bytes) out of device memory on rank %d", h->map_sizes[failed_rank], failed_rank);
+    WM_THROW(WHOLEMEMORY_CUDA_ERROR, "cuMemCreate(%zu bytes) failed on rank %d: CUDA driver error %d (%s)", h->map_sizes[failed_rank],
+             failed_rank, (int)created, cu_error_string(created));
   }
   if (share) {
     int my_fd = -1;
