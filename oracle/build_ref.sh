@@ -9,7 +9,10 @@
 # `CacheLineInfo`, and a declaration-only stand-in for RAFT's warp top-k queue
 # (ref_shim/raft/matrix/detail/select_k-inl.cuh) lets it compile; ref_optimizer_hook.cpp exposes
 # dedup + optimizer step as one extern "C" test entry.  graph_ops/ (append_unique, csr_add_self_loop) needs only
-# integer_utils and is built as is.  Embedding/cache/sampling TUs need real RAFT and are NOT built.
+# integer_utils and is built as is.  The embedding layer (wholememory/embedding*.cpp: create_embedding, optimizers,
+# gather_gradient_apply) is built as is too; only the device-cache kernels it can call (embedding_cache_func.cu,
+# gather_cached_func.cu: real RAFT select_k) are replaced by loud NOT_IMPLEMENTED stubs (ref_cache_stubs.cpp).
+# Sampling TUs need RAFT's real RNG and are NOT built.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF_ROOT:-/root/reference}"
@@ -17,7 +20,7 @@ OUT="$HERE/_ref"
 OBJ="$OUT/obj"
 [ -d "$REF/cpp/src" ] || { echo "no reference tree at $REF"; exit 3; }
 if [ -f "$OUT/libwholegraph_ref.so" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_stubs.cpp" ] \
-   && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_optimizer_hook.cpp" ]; then
+   && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_optimizer_hook.cpp" ] && [ "$OUT/libwholegraph_ref.so" -nt "$HERE/ref_cache_stubs.cpp" ]; then
   echo "oracle/_ref/libwholegraph_ref.so is up to date"; exit 0
 fi
 mkdir -p "$OBJ"
@@ -31,13 +34,14 @@ CPP="cuda_macros.cpp logger.cpp
  wholememory/wholememory_tensor.cpp wholememory/tensor_description.cpp wholememory/env_func_ptrs.cpp
  wholememory/initialize.cpp wholememory/system_info.cpp wholememory/global_reference.cpp
  wholememory_ops/gather_op.cpp wholememory_ops/scatter_op.cpp wholememory_ops/thrust_allocator.cpp
- graph_ops/append_unique.cpp graph_ops/csr_add_self_loop.cpp"
+ graph_ops/append_unique.cpp graph_ops/csr_add_self_loop.cpp
+ wholememory/embedding.cpp wholememory/embedding_optimizer.cpp wholememory/embedding_cache.cpp"
 CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl.cu
  wholememory_ops/scatter_op_impl_mapped.cu wholememory_ops/scatter_op_impl_nccl.cu
  wholememory_ops/functions/gather_func.cu wholememory_ops/functions/scatter_func.cu
  wholememory_ops/functions/bucket_ids_func.cu wholememory_ops/functions/exchange_ids_nccl_func.cu
  wholememory_ops/functions/exchange_embeddings_nccl_func.cu wholememory_ops/functions/sort_indices_func.cu
- wholememory_ops/functions/embedding_optimizer_func.cu
+ wholememory_ops/functions/embedding_optimizer_func.cu wholememory_ops/functions/map_indices_func.cu
  graph_ops/append_unique_impl.cu graph_ops/csr_add_self_loop_impl.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int32_indices.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int64_indices.cu
@@ -55,6 +59,7 @@ MK="$OBJ/Makefile"
   for f in $CU; do o="$OBJ/$(echo "$f" | tr '/' '_').o"; OBJS="$OBJS $o"; printf '%s: %s\n\t%s %s -c $< -o $@\n' "$o" "$S/$f" "$NVCC" "$NVFLAGS"; done
   o="$OBJ/ref_stubs.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_stubs.cpp" "$CXXFLAGS"
   o="$OBJ/ref_optimizer_hook.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_optimizer_hook.cpp" "$CXXFLAGS"
+  o="$OBJ/ref_cache_stubs.o"; OBJS="$OBJS $o"; printf '%s: %s\n\tg++ %s -c $< -o $@\n' "$o" "$HERE/ref_cache_stubs.cpp" "$CXXFLAGS"
   echo "objs:$OBJS"
   echo "OBJS=$OBJS"
 } > "$MK"

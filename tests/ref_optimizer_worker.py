@@ -1,9 +1,12 @@
 """Runs a fixed, seeded list of sparse-optimizer cases and dumps the resulting weights / optimizer states.
 
-Two modes, same inputs:
+Three legs, same inputs:
   * WHOLEGRAPH_B200_LIB unset  -> this repo's library through its public path
     (wholememory_embedding_gather_gradient_apply: fused duplicate merge + update kernel);
-  * WHOLEGRAPH_B200_LIB = oracle/_ref/libwholegraph_ref.so -> the REFERENCE's own dedup + optimizer kernels
+  * WHOLEGRAPH_B200_LIB = oracle/_ref/libwholegraph_ref.so, WG_OPT_WORKER_MODE=api -> the REFERENCE's whole
+    gather_gradient_apply pipeline (cpp/src/wholememory/embedding.cpp:146-323, built from /root/reference) through the
+    same public calls;
+  * WHOLEGRAPH_B200_LIB = oracle/_ref/libwholegraph_ref.so (default mode "hook") -> the REFERENCE's own dedup + optimizer kernels
     (cpp/src/wholememory_ops/functions/exchange_embeddings_nccl_func.cu:76-206, embedding_optimizer_func.cu) through
     the test hook oracle/ref_optimizer_hook.cpp, on plain device buffers laid out like the reference's embedding
     (row stride padded to 4 floats, LazyAdam state [N, 2*stride] = [m | v], per-row [beta1^t, beta2^t] starting at 1).
@@ -49,7 +52,8 @@ def case_inputs(ci):
     return w0, steps
 
 
-def run_ours(ci):
+def run_api(ci, with_states=True):
+    """Through the public C ABI (create_embedding / set_optimizer / gather_gradient_apply) of whichever library is loaded."""
     import torch
     import gpu_utils as G
     import wholegraph_b200.binding as wmb
@@ -72,7 +76,8 @@ def run_ours(ci):
                                          False, LR, env, get_stream())
     torch.cuda.synchronize()
     res = {"w": local.cpu().numpy().copy()}
-    names = {"adam": ["m", "v", "beta12t"], "adagrad": ["state_sum"], "rmsprop": ["v"], "sgd": []}[kind]
+    # the reference's get_optimizer_state views cover rows [0, D) only (embedding.cpp:336), so states are read back from this repo's library only
+    names = {"adam": ["m", "v", "beta12t"], "adagrad": ["state_sum"], "rmsprop": ["v"], "sgd": []}[kind] if with_states else []
     for nm in names:
         res[nm] = emb.get_optimizer_state(nm).get_local_tensor(wmb.MlDevice, 0)[0].cpu().numpy()[:, : (2 if nm == "beta12t" else dim)].copy()
     emb.destroy_embedding()
@@ -129,10 +134,13 @@ def run_reference(ci):
 
 
 def run_all(out_path):
-    ref_mode = bool(os.environ.get("WHOLEGRAPH_B200_LIB"))
+    """WG_OPT_WORKER_MODE: "api" (public C ABI; default for this repo's library), "hook" (the reference's dedup + optimizer
+    kernels through oracle/ref_optimizer_hook.cpp; default when WHOLEGRAPH_B200_LIB is set)."""
+    ref_lib = bool(os.environ.get("WHOLEGRAPH_B200_LIB"))
+    mode = os.environ.get("WG_OPT_WORKER_MODE", "hook" if ref_lib else "api")
     out = {}
     for ci in range(len(CASES)):
-        res = run_reference(ci) if ref_mode else run_ours(ci)
+        res = run_reference(ci) if mode == "hook" else run_api(ci, with_states=not ref_lib)
         for k, v in res.items():
             out["case%d_%s" % (ci, k)] = v
     np.savez_compressed(out_path, **out)

@@ -35,12 +35,15 @@ def _has_hook():
         return False
 
 
-def _run_worker(tmp_path, name, lib=None):
+def _run_worker(tmp_path, name, lib=None, mode=None):
     out = str(tmp_path / (name + ".npz"))
     env = dict(os.environ)
     env.pop("WHOLEGRAPH_B200_LIB", None)
+    env.pop("WG_OPT_WORKER_MODE", None)
     if lib:
         env["WHOLEGRAPH_B200_LIB"] = lib
+    if mode:
+        env["WG_OPT_WORKER_MODE"] = mode
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_optimizer_worker.py"), out], env=env,
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, "worker failed:\n" + p.stdout[-2000:] + p.stderr[-4000:]
@@ -104,3 +107,25 @@ def test_reference_optimizer_kernels_match_ours_and_the_oracle(tmp_path):
     assert sorted(ref) == sorted(ours)
     _compare(ref, ours, "this repo's fused kernel vs the reference binary")
     _compare(ref, _oracle_results(), "oracle (CPU restatement) vs the reference binary")
+
+
+def _has_embedding_api():
+    if not os.path.exists(REF_SO):
+        return False
+    try:
+        out = subprocess.run(["nm", "-D", REF_SO], capture_output=True, text=True, timeout=60).stdout
+        return " T wholememory_embedding_gather_gradient_apply" in out
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _has_embedding_api(), reason="oracle/_ref/libwholegraph_ref.so without the reference's embedding layer")
+def test_reference_gradient_apply_pipeline_matches_ours(tmp_path):
+    """The reference's WHOLE wholememory_embedding_gather_gradient_apply (bucket + NCCL exchange at world_size 1 + dedup +
+    optimizer, embedding.cpp:146-323) against this repo's, through identical public C-ABI calls; weights after 3 steps."""
+    ref_api = _run_worker(tmp_path, "ref_api", REF_SO, mode="api")
+    ours = _run_worker(tmp_path, "ours")
+    ref_api = {k: ref_api[k] for k in ref_api.files}
+    ours_w = {k: ours[k] for k in ours.files if k.endswith("_w")}
+    assert sorted(ref_api) == sorted(ours_w)
+    _compare(ref_api, ours_w, "this repo's gradient apply vs the reference's pipeline (weights)")

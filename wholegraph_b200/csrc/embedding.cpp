@@ -340,7 +340,11 @@ wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* w
     padded.strides[0]     = wm::pad_to_16_bytes(md.sizes[1], wholememory_dtype_get_element_size(md.dtype));
     WHOLEMEMORY_RETURN_ON_FAIL(wholememory_create_tensor(&e->allocated, &padded, comm, memory_type, memory_location, embedding_entry_partition));
     int64_t starts[2] = {0, 0}, ends[2] = {md.sizes[0], md.sizes[1]};
-    WHOLEMEMORY_RETURN_ON_FAIL(wholememory_tensor_get_subtensor(e->allocated, starts, ends, &e->user));
+    wholememory_error_code_t rc = wholememory_tensor_get_subtensor(e->allocated, starts, ends, &e->user);
+    if (rc != WHOLEMEMORY_SUCCESS) {
+      (void)wholememory_destroy_tensor(e->allocated); /* collective like the creation: every rank takes this branch */
+      return rc;
+    }
     *wholememory_embedding = e.release();
     return WHOLEMEMORY_SUCCESS;
   });
