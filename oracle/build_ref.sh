@@ -12,7 +12,9 @@
 # integer_utils and is built as is.  The embedding layer (wholememory/embedding*.cpp: create_embedding, optimizers,
 # gather_gradient_apply) is built as is too; only the device-cache kernels it can call (embedding_cache_func.cu,
 # gather_cached_func.cu: real RAFT select_k) are replaced by loud NOT_IMPLEMENTED stubs (ref_cache_stubs.cpp).
-# Sampling TUs need RAFT's real RNG and are NOT built.
+# The UNWEIGHTED sampler (wholegraph_ops/unweighted_*, raft_random_gen.cu) is built as is on top of a RESTATED PCG generator
+# (ref_shim/raft/random/rng_device.cuh -- same stream as oracle/wm_oracle.c, not verified against RAFT): the reference's
+# selection kernels are real, the random stream is the restated one.  The weighted sampler needs RAFT's select_k: NOT built.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF_ROOT:-/root/reference}"
@@ -35,7 +37,8 @@ CPP="cuda_macros.cpp logger.cpp
  wholememory/initialize.cpp wholememory/system_info.cpp wholememory/global_reference.cpp
  wholememory_ops/gather_op.cpp wholememory_ops/scatter_op.cpp wholememory_ops/thrust_allocator.cpp
  graph_ops/append_unique.cpp graph_ops/csr_add_self_loop.cpp
- wholememory/embedding.cpp wholememory/embedding_optimizer.cpp wholememory/embedding_cache.cpp"
+ wholememory/embedding.cpp wholememory/embedding_optimizer.cpp wholememory/embedding_cache.cpp
+ wholegraph_ops/unweighted_sample_without_replacement.cpp"
 CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl.cu
  wholememory_ops/scatter_op_impl_mapped.cu wholememory_ops/scatter_op_impl_nccl.cu
  wholememory_ops/functions/gather_func.cu wholememory_ops/functions/scatter_func.cu
@@ -43,6 +46,8 @@ CU="wholememory_ops/gather_op_impl_mapped.cu wholememory_ops/gather_op_impl_nccl
  wholememory_ops/functions/exchange_embeddings_nccl_func.cu wholememory_ops/functions/sort_indices_func.cu
  wholememory_ops/functions/embedding_optimizer_func.cu wholememory_ops/functions/map_indices_func.cu
  graph_ops/append_unique_impl.cu graph_ops/csr_add_self_loop_impl.cu
+ wholegraph_ops/unweighted_sample_without_replacement_impl_mapped.cu
+ wholegraph_ops/unweighted_sample_without_replacement_impl_nccl.cu wholegraph_ops/raft_random_gen.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int32_indices.cu
  wholememory_ops/functions/gather_func_impl_floating_data_int64_indices.cu
  wholememory_ops/functions/gather_func_impl_integer_data_int32_indices.cu
