@@ -363,7 +363,11 @@ def main():
                                               "into oracle/_ref, same config, same harness; the reference path runs on the GPU, one host thread drives it"}
             line["e2e"] = line.get("e2e") or {"value": round(out_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         elif not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(dim, esize, np.float32 if esize == 4 else np.float16)
+            try:
+                line["cpu_baseline"] = cpu_baseline(dim, esize, np.float32 if esize == 4 else np.float16)
+            except Exception as ex:  # the GPU measurement above must not be lost to a host-side problem
+                line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": "unavailable: %r" % (ex,)}
         print(json.dumps(line), flush=True)
 
     wmb.destroy_wholememory_tensor(table)
