@@ -116,3 +116,29 @@ def test_native_env_matches_python_callbacks_on_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, os.path.join(root, "tests", "native_env_worker.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "native env worker OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+def test_python_callback_table_protocol_host():
+    """The DEFAULT env table (ctypes closures over torch) follows the same protocol; exercised here without a GPU
+    through HOST allocations, exactly as the library calls it."""
+    wenv.unload_native_env()
+    env = _env_table(wenv.get_wholegraph_env_fns())
+    ctx = ctypes.c_void_p()
+    env.temporary_fns.create_memory_context_fn(ctypes.byref(ctx), None)
+    assert ctx.value
+    d = _desc((3, 4), 6)
+    ptr = env.temporary_fns.malloc_fn(ctypes.byref(d), 2, ctx, None)
+    assert ptr
+    t = wenv.TorchMemoryContext._live[ctx.value].get_tensor()
+    assert t.shape == (3, 4) and t.dtype == torch.int64 and t.data_ptr() == ptr
+    env.temporary_fns.free_fn(ctx, None)
+    assert wenv.TorchMemoryContext._live[ctx.value].get_tensor() is None
+    env.temporary_fns.destroy_memory_context_fn(ctx, None)
+    assert ctx.value not in wenv.TorchMemoryContext._live
+    # caller-owned output context
+    c = wenv.TorchMemoryContext()
+    d = _desc((9,), 1)
+    ptr = env.output_fns.malloc_fn(ctypes.byref(d), 2, c.get_c_context(), None)
+    assert c.get_tensor().data_ptr() == ptr and c.get_tensor().dtype == torch.float32
+    c.free()
+    assert id(c) not in wenv.TorchMemoryContext._live
