@@ -236,10 +236,13 @@ def main():
         sampler.start()
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     ev0.record(stream)
     for i in range(args.steps):
         step(i)
     ev1.record(stream)
+    torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # the reference bench's own clock: wall time over K calls + one sync
     sync_all()
     ms = ev0.elapsed_time(ev1) / args.steps
     # keep the GPU busy a little longer so the clock sampler sees the loaded state even for tiny K
@@ -353,6 +356,9 @@ def main():
                        "l2": "inputs larger than L2: table %.0f GB, 8 distinct index batches cycled, 1 GB output per step" % (rows_total * row / 1e9),
                        "rows_per_gpu": args.rows_per_gpu, "embedding_dim": dim, "indices_per_rank": n, "memory_type": mem_type},
             "roofline": roof, "gpu_launches": args.steps, "clocks": clocks,
+            "host_timed": {"value": round(n * row * world / (host_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(host_ms, 4),
+                           "how": "rank 0 wall clock over the K back-to-back calls + one device synchronize: the reference bench's "
+                                  "definition (cpp/bench/wholememory_ops/gather_scatter_bench.cu:363-366); informational"},
         }
         if e2e:
             line["e2e"] = e2e
