@@ -43,6 +43,18 @@ def _worker(rank, world_size, port, results):
         comm2 = wgth.create_group_communicator()
         assert comm2.get_rank() == rank
         wgth.destroy_communicator(comm2)
+        # strided groups (reference comm.py:133): 4 ranks, group_size 2, stride 2 -> [0, 2] and [1, 3]
+        if world_size == 4:
+            g = wgth.create_group_communicator(2, 2)
+            assert g.get_size() == 2 and g.get_rank() == rank // 2
+            g.barrier()
+            wgth.destroy_communicator(g)
+            g = wgth.create_group_communicator(2, 1)  # [0, 1] and [2, 3]
+            assert g.get_size() == 2 and g.get_rank() == rank % 2
+            g.barrier()
+            wgth.destroy_communicator(g)
+            dev = wgth.get_local_device_communicator()
+            assert dev.get_size() == 1 and dev.get_rank() == 0 and wgth.get_local_device_communicator() is dev
         # collective argument check: different sizes on different ranks must be rejected, not deadlock
         if not torch.cuda.is_available():
             try:
@@ -63,7 +75,7 @@ def _worker(rank, world_size, port, results):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("world_size", [2, 3])
+@pytest.mark.parametrize("world_size", [2, 3, 4])
 def test_control_plane_world_size_n_over_gloo(world_size):
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
