@@ -62,3 +62,18 @@ def test_builtin_cache_policy_argument_checks():
         wgth.create_builtin_cache_policy("everywhere", "chunked", "cuda", "readonly", 0.5)
     with pytest.raises(ValueError):
         wgth.create_builtin_cache_policy("local_device", "chunked", "cuda", "readonly", 0.5, cache_memory_location="disk")
+
+
+def test_file_entry_counting(tmp_path):
+    from wholegraph_b200.torch.utils import count_file_entries, get_part_file_list
+    names = get_part_file_list(str(tmp_path / "feat"), 3)
+    assert [n.rsplit("/", 1)[1] for n in names] == ["feat_part_0_of_3", "feat_part_1_of_3", "feat_part_2_of_3"]
+    for i, n in enumerate(names):
+        with open(n, "wb") as f:
+            f.write(b"\0" * (64 * (i + 1)))
+    assert count_file_entries(names, 64) == 6
+    assert count_file_entries(names, 4) == 96
+    with pytest.raises(ValueError):
+        count_file_entries(names, 48)
+    with pytest.raises(ValueError):
+        count_file_entries([str(tmp_path / "missing")], 4)

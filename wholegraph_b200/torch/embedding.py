@@ -19,32 +19,36 @@ from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tenso
 
 
 class WholeMemoryOptimizer(object):
-    """Sparse optimizer shared by any number of WholeMemoryEmbeddings; create with create_wholememory_optimizer."""
+    """One sparse optimizer (SGD / LazyAdam / AdaGrad / RMSProp) driving any number of WholeMemoryEmbeddings.
+    Build it with create_wholememory_optimizer; call step(lr) once per training iteration on every rank."""
 
     def __init__(self, global_comm: WholeMemoryCommunicator):
         super().__init__()
+        self.global_comm = global_comm
         self.wmb_opt = wmb.WholeMemoryOptimizer()
         self.embeddings = []
-        self.global_comm = global_comm
 
     def add_embedding(self, wm_embedding):
+        """Attach the optimizer (allocates its state tensors, collectively).  An embedding takes one optimizer, once."""
         assert isinstance(wm_embedding, WholeMemoryEmbedding)
         if wm_embedding.wmb_optimizer is not None:
             raise ValueError("optimizer can only be set once.")
-        wm_embedding.wmb_optimizer = self.wmb_opt
-        wm_embedding.dummy_input.requires_grad_(True)
         self.wmb_opt.add_embedding(wm_embedding.wmb_embedding)
+        wm_embedding.wmb_optimizer = self.wmb_opt
+        wm_embedding.dummy_input.requires_grad_(True)  # lets autograd reach EmbeddingLookupFn.backward
         self.embeddings.append(wm_embedding)
 
     def step(self, lr: float):
-        """Apply the accumulated sparse gradients of every embedding, then barrier."""
-        for wm_embedding in self.embeddings:
-            if wm_embedding.need_apply:
-                wm_embedding.apply_gradients(lr)
+        """Push every embedding's pending sparse gradients to their owners and update the rows, then barrier so that
+        no rank reads a row another rank is still updating."""
+        for pending in (e for e in self.embeddings if e.need_apply):
+            pending.apply_gradients(lr)
         self.global_comm.barrier()
 
 
 class WholeMemoryCachePolicy(object):
+    """Python handle of a wholememory_embedding_cache_policy_t (kept for API compatibility, see the module docstring)."""
+
     def __init__(self, wmb_cache_policy: wmb.WholeMemoryCachePolicy):
         super().__init__()
         self.wmb_cache_policy = wmb_cache_policy
@@ -52,10 +56,10 @@ class WholeMemoryCachePolicy(object):
 
 def create_wholememory_cache_policy(cache_comm: WholeMemoryCommunicator, *, memory_type: str = "chunked",
                                     memory_location: str = "cuda", access_type: str = "readonly", ratio: float = 0.5):
-    p = wmb.WholeMemoryCachePolicy()
-    p.create_policy(cache_comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
-                    str_to_wmb_wholememory_location(memory_location), str_to_wmb_wholememory_access_type(access_type), ratio)
-    return WholeMemoryCachePolicy(p)
+    policy = wmb.WholeMemoryCachePolicy()
+    policy.create_policy(cache_comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
+                         str_to_wmb_wholememory_location(memory_location), str_to_wmb_wholememory_access_type(access_type), ratio)
+    return WholeMemoryCachePolicy(policy)
 
 
 def destroy_wholememory_cache_policy(cache_policy: WholeMemoryCachePolicy):
@@ -99,80 +103,80 @@ def create_builtin_cache_policy(builtin_cache_type: str, embedding_memory_type: 
 
 
 class EmbeddingLookupFn(torch.autograd.Function):
+    """autograd bridge: forward = gather; backward hands (indices, dL/d rows) to the embedding, which keeps them until
+    WholeMemoryOptimizer.step.  `dummy_input` is a 1-element parameter whose only job is to make this node differentiable."""
+
     @staticmethod
     def forward(ctx, indice: torch.Tensor, dummy_input: torch.Tensor, wm_embedding, is_training: bool = False,
                 force_dtype: Union[torch.dtype, None] = None):
-        output_tensor = wm_embedding.gather(indice, is_training=is_training, force_dtype=force_dtype)
+        rows = wm_embedding.gather(indice, is_training=is_training, force_dtype=force_dtype)
         if is_training and wm_embedding.need_grad():
-            ctx.save_for_backward(indice, output_tensor, dummy_input)
             ctx.wm_embedding = wm_embedding
-        return output_tensor
+            ctx.save_for_backward(indice, rows, dummy_input)
+        return rows
 
     @staticmethod
     def backward(ctx, grad_outputs: torch.Tensor):
-        indice, output_tensor, dummy_input = ctx.saved_tensors
-        wm_embedding = ctx.wm_embedding
-        wm_embedding.add_gradients(indice, grad_outputs)
+        indice, _rows, dummy_input = ctx.saved_tensors
+        ctx.wm_embedding.add_gradients(indice, grad_outputs)
         ctx.wm_embedding = None
         return None, torch.zeros_like(dummy_input), None, None, None
 
 
 class WholeMemoryEmbedding(object):
-    r"""WholeMemory Embedding"""
+    """An [N, D] embedding table in WholeMemory, trainable once an optimizer is attached."""
 
     def __init__(self, wmb_embedding: wmb.PyWholeMemoryEmbedding, wmb_cache_policy: Union[WholeMemoryCachePolicy, None]):
         super().__init__()
         self.wmb_embedding = wmb_embedding
-        self.embedding_tensor = None
-        self.optimizer_states = dict()
         self.wmb_cache_policy = wmb_cache_policy
-        self.adjust_cache = self.wmb_cache_policy is not None
+        self.adjust_cache = wmb_cache_policy is not None
         self.wmb_optimizer = None
         self.dummy_input = torch.nn.Parameter(torch.zeros(1), requires_grad=False)
+        # lazily created views
+        self.embedding_tensor = None
+        self.optimizer_states = {}
+        # sparse gradients recorded by backward passes since the last apply
+        self.sparse_indices, self.sparse_grads = [], []
         self.need_apply = False
-        self.sparse_indices = []
-        self.sparse_grads = []
-
-    def dim(self):
-        return self.get_embedding_tensor().dim()
 
     @property
     def shape(self):
         return self.get_embedding_tensor().shape
 
+    def dim(self):
+        return self.get_embedding_tensor().dim()
+
     def set_adjust_cache(self, adjust_cache: bool):
-        self.adjust_cache = adjust_cache if self.wmb_cache_policy is not None else False
+        self.adjust_cache = bool(adjust_cache) and self.wmb_cache_policy is not None
 
     def need_grad(self):
         return self.wmb_optimizer is not None
 
     def gather(self, indice: torch.Tensor, *, is_training: bool = False, force_dtype: Union[torch.dtype, None] = None):
+        """rows[i, :] = table[indice[i], :] on the current CUDA device; with is_training and an optimizer attached the
+        result requires grad and the embedding is marked as having gradients to apply at the next optimizer step."""
         assert indice.dim() == 1
-        embedding_dim = self.get_embedding_tensor().shape[1]
-        embedding_count = indice.shape[0]
-        current_cuda_device = "cuda:%d" % (torch.cuda.current_device(),)
-        output_dtype = force_dtype if force_dtype is not None else self.embedding_tensor.dtype
-        need_grad = self.need_grad() and is_training
-        output_tensor = torch.empty([embedding_count, embedding_dim], device=current_cuda_device, dtype=output_dtype,
-                                    requires_grad=need_grad)
-        if need_grad:
+        table = self.get_embedding_tensor()
+        track = is_training and self.need_grad()
+        rows = torch.empty([indice.shape[0], table.shape[1]], device="cuda:%d" % torch.cuda.current_device(),
+                           dtype=table.dtype if force_dtype is None else force_dtype, requires_grad=track)
+        if track:
             self.need_apply = True
-        wmb.EmbeddingGatherForward(self.wmb_embedding, wrap_torch_tensor(indice), wrap_torch_tensor(output_tensor),
-                                   self.adjust_cache, get_wholegraph_env_fns(), get_stream())
-        return output_tensor
+        wmb.EmbeddingGatherForward(self.wmb_embedding, wrap_torch_tensor(indice), wrap_torch_tensor(rows), self.adjust_cache,
+                                   get_wholegraph_env_fns(), get_stream())
+        return rows
 
     def add_gradients(self, indice: torch.Tensor, grad_outputs: torch.Tensor):
         self.sparse_indices.append(indice)
         self.sparse_grads.append(grad_outputs)
 
     def apply_gradients(self, lr: float):
-        sparse_indices = torch.cat(self.sparse_indices)
-        sparse_grads = torch.cat(self.sparse_grads)
-        wmb.EmbeddingGatherGradientApply(self.wmb_embedding, wrap_torch_tensor(sparse_indices),
-                                         wrap_torch_tensor(sparse_grads), self.adjust_cache, lr,
-                                         get_wholegraph_env_fns(), get_stream())
-        self.sparse_indices = []
-        self.sparse_grads = []
+        """One wholememory_embedding_gather_gradient_apply over everything recorded since the last call (collective)."""
+        indices, grads = torch.cat(self.sparse_indices), torch.cat(self.sparse_grads)
+        self.sparse_indices, self.sparse_grads = [], []
+        wmb.EmbeddingGatherGradientApply(self.wmb_embedding, wrap_torch_tensor(indices), wrap_torch_tensor(grads), self.adjust_cache,
+                                         lr, get_wholegraph_env_fns(), get_stream())
         self.need_apply = False
 
     def writeback_all_cache(self):
@@ -190,10 +194,10 @@ class WholeMemoryEmbedding(object):
         return self.wmb_embedding.get_optimizer_state_names()
 
     def get_optimizer_state(self, state_name):
-        if state_name not in self.optimizer_states:
-            self.optimizer_states[state_name] = WholeMemoryTensor(self.wmb_embedding.get_optimizer_state(state_name))
-        return self.optimizer_states[state_name]
-
+        state = self.optimizer_states.get(state_name)
+        if state is None:
+            state = self.optimizer_states[state_name] = WholeMemoryTensor(self.wmb_embedding.get_optimizer_state(state_name))
+        return state
 
     def save(self, file_prefix: str):
         """Checkpoint the embedding rows and every optimizer state (one part file per rank and tensor)."""
@@ -212,28 +216,32 @@ def create_embedding(comm: WholeMemoryCommunicator, memory_type: str, memory_loc
                      sizes: List[int], *, cache_policy: Union[WholeMemoryCachePolicy, None] = None,
                      embedding_entry_partition: Union[List[int], None] = None, random_init: bool = False,
                      gather_sms: int = -1, round_robin_size: int = 0):
-    """Create a [sizes[0], sizes[1]] embedding table row-sharded over comm."""
-    wmb_cache_policy = wmb.create_non_cache_policy() if cache_policy is None else cache_policy.wmb_cache_policy
+    """Create a [sizes[0], sizes[1]] embedding table row-sharded over comm (collective; ends with a barrier).
+
+    embedding_entry_partition[i] = rows owned by rank i; it is dropped (with a note) when a cache policy is given, and it
+    switches round-robin sharding off.  random_init fills this rank's rows with Xavier-uniform values.  gather_sms limits
+    the SMs a gather may use (-1 = all)."""
     assert len(sizes) == 2
-    tensor_desc = wmb.PyWholeMemoryTensorDescription()
-    tensor_desc.set_dtype(torch_dtype_to_wholememory_dtype(dtype))
-    tensor_desc.set_shape(sizes)
-    tensor_desc.set_stride([sizes[1], 1])
-    if embedding_entry_partition is not None and cache_policy is not None:
-        print("embedding_entry_partition is ignored because cache_policy is specified")
-        embedding_entry_partition = None
-    if embedding_entry_partition is not None and round_robin_size != 0:
-        print("round_robin_size is ignored because embedding_entry_partition is specified")
-        round_robin_size = 0
-    wm_embedding = WholeMemoryEmbedding(
-        wmb.create_embedding(tensor_desc, comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
-                             str_to_wmb_wholememory_location(memory_location), wmb_cache_policy,
-                             embedding_entry_partition=embedding_entry_partition, user_defined_sms=gather_sms,
-                             round_robin_size=round_robin_size),
-        cache_policy)
+    if embedding_entry_partition is not None:
+        if cache_policy is not None:
+            print("[wholegraph_b200] a cache policy decides the row partition itself: embedding_entry_partition dropped")
+            embedding_entry_partition = None
+        elif round_robin_size != 0:
+            print("[wholegraph_b200] an explicit embedding_entry_partition excludes round-robin sharding: round_robin_size set to 0")
+            round_robin_size = 0
+    desc = wmb.PyWholeMemoryTensorDescription()
+    desc.set_dtype(torch_dtype_to_wholememory_dtype(dtype))
+    desc.set_shape(sizes)
+    desc.set_stride([sizes[1], 1])
+    policy = cache_policy.wmb_cache_policy if cache_policy is not None else wmb.create_non_cache_policy()
+    handle = wmb.create_embedding(desc, comm.wmb_comm, str_to_wmb_wholememory_memory_type(memory_type),
+                                  str_to_wmb_wholememory_location(memory_location), policy,
+                                  embedding_entry_partition=embedding_entry_partition, user_defined_sms=gather_sms,
+                                  round_robin_size=round_robin_size)
+    wm_embedding = WholeMemoryEmbedding(handle, cache_policy)
     if random_init is True:
-        local_tensor, local_offset = wm_embedding.get_embedding_tensor().get_local_tensor()
-        torch.nn.init.xavier_uniform_(local_tensor)
+        my_rows, _first_row = wm_embedding.get_embedding_tensor().get_local_tensor()
+        torch.nn.init.xavier_uniform_(my_rows)
     comm.barrier()
     return wm_embedding
 
@@ -268,7 +276,8 @@ def destroy_embedding(wm_embedding: WholeMemoryEmbedding):
 
 
 class WholeMemoryEmbeddingModule(torch.nn.Module):
-    """torch.nn.Module wrapper of WholeMemoryEmbedding."""
+    """nn.Module face of a WholeMemoryEmbedding: forward(indices) -> rows, differentiable while the module is in
+    training mode and the embedding has an optimizer."""
 
     def __init__(self, wm_embedding: WholeMemoryEmbedding):
         super().__init__()
@@ -276,18 +285,19 @@ class WholeMemoryEmbeddingModule(torch.nn.Module):
         self.embedding_gather_fn = EmbeddingLookupFn.apply
 
     def forward(self, indice: torch.Tensor, force_dtype: Union[torch.dtype, None] = None):
-        return self.embedding_gather_fn(indice, self.wm_embedding.dummy_input, self.wm_embedding, self.training, force_dtype)
+        emb = self.wm_embedding
+        return self.embedding_gather_fn(indice, emb.dummy_input, emb, self.training, force_dtype)
 
 
 def create_wholememory_optimizer(embeddings: Union[WholeMemoryEmbedding, List[WholeMemoryEmbedding]], optimizer_type: str,
                                  param_dict: dict, global_comm: Union[WholeMemoryCommunicator, None] = None):
-    wm_optimizer = WholeMemoryOptimizer(global_comm if global_comm is not None else get_global_communicator())
+    """optimizer_type: "sgd" | "adam" (LazyAdam; adam_w=1 for AdamW) | "adagrad" | "rmsprop"; param_dict holds the float
+    parameters by the reference's names (weight_decay, epsilon, beta1, beta2, adam_w, alpha).  global_comm (optional here,
+    the global communicator by default) is what WholeMemoryOptimizer.step barriers on."""
+    wm_optimizer = WholeMemoryOptimizer(get_global_communicator() if global_comm is None else global_comm)
     wm_optimizer.wmb_opt.create_optimizer(str_to_wmb_wholememory_optimizer_type(optimizer_type), param_dict)
-    if isinstance(embeddings, WholeMemoryEmbedding):
-        wm_optimizer.add_embedding(embeddings)
-    else:
-        for em in embeddings:
-            wm_optimizer.add_embedding(em)
+    for emb in ([embeddings] if isinstance(embeddings, WholeMemoryEmbedding) else embeddings):
+        wm_optimizer.add_embedding(emb)
     return wm_optimizer
 
 

@@ -93,3 +93,15 @@ def get_part_file_name(prefix: str, part_id: int, part_count: int):
 
 def get_part_file_list(prefix: str, part_count: int):
     return [get_part_file_name(prefix, part_id, part_count) for part_id in range(part_count)]
+
+
+def count_file_entries(filelist, entry_bytes: int) -> int:
+    """Entries of `entry_bytes` bytes held by a list of raw binary files; every file must hold a whole number of them
+    (the rule both file-backed constructors of the reference apply, tensor.py:276-287 / embedding.py:498-509)."""
+    total = 0
+    for filename in filelist:
+        size = get_file_size(filename)
+        if size % entry_bytes != 0:
+            raise ValueError("File %s size is %d not mutlple of %d" % (filename, size, entry_bytes))
+        total += size
+    return total // entry_bytes
