@@ -47,3 +47,7 @@ WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 600 python tools/be
 timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
 WG_TORCH_NATIVE_ENV=1 timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
 ls -la gpurun_out | tail -12
+
+step "5. sanitizers on the smoke pass (every kernel of the hot path once; SURVEY section 5)"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_$R.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|smoke OK" gpurun_out/sanitizer_memcheck_$R.log | tail -3
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_$R.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|smoke OK" gpurun_out/sanitizer_racecheck_$R.log | tail -3
