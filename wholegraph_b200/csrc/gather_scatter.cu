@@ -61,6 +61,7 @@ template <typename IdxT, bool GATHER>
 void launch_vec_w(int vec, const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
 {
   switch (vec) {
+    case 32: launch_vec<IdxT, 32, GATHER>(t, g, idx, n, dense, grid, s); break;
     case 16: launch_vec<IdxT, 16, GATHER>(t, g, idx, n, dense, grid, s); break;
     case 8: launch_vec<IdxT, 8, GATHER>(t, g, idx, n, dense, grid, s); break;
     case 4: launch_vec<IdxT, 4, GATHER>(t, g, idx, n, dense, grid, s); break;
@@ -214,7 +215,10 @@ void row_move(bool gather,
 
   if (td.dtype == dd.dtype) {
     const int64_t row_bytes = td.sizes[1] * et;
-    int vec                 = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, 16);
+    /* widest unit: 16 bytes; WG_VEC32=1 (developer knob, not yet measured) tries sm_100's 256-bit accesses where every
+     * address, stride and the row size are multiples of 32 bytes */
+    static const int max_vec = env_int("WG_VEC32", 0) != 0 ? 32 : 16;
+    int vec                 = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, max_vec);
     g.row_elems             = (int)td.sizes[1];
     set_units(&g, row_bytes / vec);
     int grid                = 1;

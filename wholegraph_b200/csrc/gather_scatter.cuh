@@ -64,6 +64,14 @@ __device__ __forceinline__ char* resolve_table_byte(const table_ref& t, uint64_t
 /* ---- vector moves with streaming cache hints ---- */
 template <int BYTES>
 struct vec_t;
+/* 32-byte unit: sm_100 has 256-bit global loads/stores (SASS LDG.E.256 / STG.E.256).  Experiment knob WG_VEC32=1. */
+struct alignas(32) u32x8 {
+  uint32_t v[8];
+};
+template <>
+struct vec_t<32> {
+  using type = u32x8;
+};
 template <>
 struct vec_t<16> {
   using type = uint4;
@@ -107,6 +115,24 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p)
 __device__ __forceinline__ uint16_t ld_stream(const uint16_t* p) { return *p; }
 __device__ __forceinline__ uint8_t ld_stream(const uint8_t* p) { return *p; }
 
+__device__ __forceinline__ u32x8 ld_stream(const u32x8* p)
+{
+  u32x8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+/* L1-allocating form, used when rows can be remote (same choice as the 16-byte path's policy 2) */
+__device__ __forceinline__ u32x8 ld_plain(const u32x8* p)
+{
+  u32x8 r;
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
 /* experiment variants of the 16-byte accesses, selected by row_geom::policy (warp-uniform) */
 __device__ __forceinline__ uint4 ld_variant(const uint4* p, int variant)
 {
@@ -135,6 +161,18 @@ __device__ __forceinline__ void st_variant(uint4* p, uint4 v, int variant)
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v)
 {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(u32x8* p, const u32x8& r)
+{
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+               "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_plain(u32x8* p, const u32x8& r)
+{
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+               "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
 }
 __device__ __forceinline__ void st_stream(uint2* p, uint2 v)
 {
@@ -221,6 +259,8 @@ __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
         if (live) {
           if (GATHER) {
             if constexpr (VEC == 16) val[u] = ld_variant(reinterpret_cast<const uint4*>(tp), g.policy & 15);
+            else if constexpr (VEC == 32)
+              val[u] = (g.policy & 15) == 2 ? ld_plain(reinterpret_cast<const u32x8*>(tp)) : ld_stream(reinterpret_cast<const u32x8*>(tp));
             else val[u] = ld_stream(reinterpret_cast<const V*>(tp));
             dst[u] = dp;
           } else {
@@ -235,8 +275,10 @@ __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
           if (GATHER) {
             if constexpr (VEC == 16) st_variant(reinterpret_cast<uint4*>(dst[u]), val[u], g.policy >> 4);
             else st_stream(reinterpret_cast<V*>(dst[u]), val[u]);
-          } else
-            *reinterpret_cast<V*>(dst[u]) = val[u];
+          } else {
+            if constexpr (VEC == 32) st_plain(reinterpret_cast<u32x8*>(dst[u]), val[u]);
+            else *reinterpret_cast<V*>(dst[u]) = val[u];
+          }
         }
       }
     }
