@@ -10,7 +10,7 @@ step() { echo "=== $*"; }
 step "1. full GPU suite (incl. tests/test_zz_*: native env, reference-binary optimizer + graph-ops parity, full-size configs)"
 timeout 1500 python -X faulthandler -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$R.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_$R.log | cut -c1-300
 # if -x stopped early, still learn what the new files do on their own
-for f in tests/test_cpp_abi.py tests/test_zz_native_env.py tests/test_zz_ref_optimizer_parity_gpu.py tests/test_zz_ref_graph_ops_parity_gpu.py tests/test_zz_ref_sampling_parity_gpu.py tests/test_zz_reference_binding_full_gpu.py tests/test_zz_baseline_configs_gpu.py; do
+for f in tests/test_cpp_abi.py tests/test_zz_native_env.py tests/test_zz_ref_optimizer_parity_gpu.py tests/test_zz_ref_graph_ops_parity_gpu.py tests/test_zz_ref_sampling_parity_gpu.py tests/test_zz_reference_binding_full_gpu.py tests/test_zz_vec32_gather_gpu.py tests/test_zz_baseline_configs_gpu.py; do
   timeout 900 python -X faulthandler -m pytest $f -m gpu -q -s > gpurun_out/$(basename $f .py)_$R.log 2>&1; echo "$f rc=$?"; grep -E "bit-identical|passed|failed|Error" gpurun_out/$(basename $f .py)_$R.log | tail -6 | cut -c1-300
 done
 
@@ -18,6 +18,11 @@ step "2. smoke + both bench arms"
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --impl reference > gpurun_out/bench_reference_$R.json 2> gpurun_out/bench_reference_$R.err; tail -1 gpurun_out/bench_reference_$R.json | cut -c1-400
 timeout 900 python bench.py > gpurun_out/bench_ours_$R.json 2> gpurun_out/bench_ours_$R.err; tail -1 gpurun_out/bench_ours_$R.json | cut -c1-1800
+
+echo "-- A/B: 256-bit accesses (WG_VEC32=1), C2 and the 256-byte-row shape"
+WG_VEC32=1 timeout 600 python bench.py --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-330
+timeout 600 python bench.py --no-e2e --no-cpu-baseline --dim 128 --dtype fp16 --rows-per-gpu 125000000 2>/dev/null | tail -1 | cut -c1-330
+WG_VEC32=1 timeout 600 python bench.py --no-e2e --no-cpu-baseline --dim 128 --dtype fp16 --rows-per-gpu 125000000 2>/dev/null | tail -1 | cut -c1-330
 
 step "3. ncu: launch list of the bench command + one full capture of the gather kernel"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_bench_c2.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
