@@ -138,7 +138,14 @@ def cpu_baseline(dim, esize, np_dtype, budget_s=12.0):
         t_total += dt
         passes += 1
         best = max(best, n * dim * esize / dt / 1e9)
-    return {"value": round(best, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+    numpy_take = None
+    try:  # single-thread numpy.take as the "numpy-index reference"
+        t0 = time.perf_counter()
+        np.take(table, idx, axis=0, out=out)
+        numpy_take = round(n * dim * esize / (time.perf_counter() - t0) / 1e9, 3)
+    except Exception:
+        pass
+    return {"value": round(best, 3), "unit": "GB/s", "cores": cores, "kind": "port", "numpy_take_1_thread_gbs": numpy_take,
             "sample": "%d passes of %d random rows x %d B from a %d-row %s host table (oracle_gather_mt, %d threads, best pass)"
                       % (passes, n, dim * esize, rows, "pinned (cudaHostAlloc)" if pinned else "pageable", cores)}
 
