@@ -9,7 +9,7 @@
  *                             env-function protocol, and "device ops fail loudly without a GPU"
  *   abi_cpp_test gpu [ranks]  gather / scatter / SGD step / neighbor sampling on cuda:0, `ranks` forked processes sharing
  *                             the GPU for the mapped memory types; results checked on the host with closed forms
- * Exit code = number of failed checks.  Built and run by tests/test_cpp_abi.py.
+ * Exit code = number of failed checks.  Built and run by tests/test_zz_cpp_abi.py.
  */
 #include <wholememory/embedding.h>
 #include <wholememory/env_func_ptrs.h>
