@@ -53,6 +53,12 @@ timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
 WG_TORCH_NATIVE_ENV=1 timeout 600 python tools/bench_sample_multi.py 2>&1 | tail -1
 ls -la gpurun_out | tail -12
 
+step "4b. C++ bench with the reference's command line, same binary on both libraries (config C2)"
+B=wholegraph_b200/lib/gather_scatter_bench
+[ -x $B ] || g++ -std=c++17 -O2 -Iinclude -I/usr/local/cuda/include tools/gather_scatter_bench.cpp -o $B -L/usr/local/cuda/lib64 -lcudart -ldl
+timeout 600 $B -t 1 -l 1 -e 102400000000 -g 1073741824 -d 256 -c 20 -n 1 2>&1 | tail -3
+timeout 600 $B -t 1 -l 1 -e 102400000000 -g 1073741824 -d 256 -c 20 -n 1 --lib oracle/_ref/libwholegraph_ref.so 2>&1 | tail -3
+
 step "5. sanitizers on the smoke pass (every kernel of the hot path once; SURVEY section 5)"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_$R.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|smoke OK" gpurun_out/sanitizer_memcheck_$R.log | tail -3
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_$R.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|smoke OK" gpurun_out/sanitizer_racecheck_$R.log | tail -3
