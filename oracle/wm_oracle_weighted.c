@@ -49,12 +49,28 @@ static float key_from_weight(double weight, wpcg_t* g)
   return (log1pf(u) / logf(2.0f)) * (1.0f / (float)weight);
 }
 
-/* raft_random_gen.cu:73-108 with weight 1 (float arithmetic) */
+/* The reference's HOST replay of the key stream, raft_random_gen.cu:73-119: same draws as key_from_weight with weight 1,
+ * but the final step is DOUBLE arithmetic -- log1p(u) / log(2.0), rounded once to float -- not the device kernels'
+ * log1pf(u) / logf(2.0).  Pinned against the reference source compiled for the CPU (tests/test_ref_host_random.py). */
 void oracle_exponential_negative_floats(uint64_t seed, uint64_t subsequence, float* out, int64_t count)
 {
   wpcg_t g;
   wpcg_init(&g, seed, subsequence);
-  for (int64_t i = 0; i < count; ++i) out[i] = key_from_weight(1.0, &g);
+  for (int64_t i = 0; i < count; ++i) {
+    float u = (float)(wpcg_next(&g) >> 8) / 16777216.0f;
+    u       = (float)-(0.5 + 0.5 * (double)u);
+    uint64_t r2 = 0;
+    int rounds  = -1;
+    do {
+      uint64_t lo = wpcg_next(&g);
+      uint64_t hi = wpcg_next(&g);
+      r2          = lo | (hi << 32);
+      ++rounds;
+    } while (r2 == 0);
+    int one_bit = __builtin_clzll(r2) + rounds * 64;
+    u           = (float)((double)u * pow(2.0, (double)-one_bit));
+    out[i]      = (float)(log1p((double)u) / log(2.0));
+  }
 }
 
 typedef struct {

@@ -24,6 +24,7 @@
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <cfloat>
+#include <cmath>
 
 namespace wm {
 namespace {
@@ -387,7 +388,25 @@ wholememory_error_code_t generate_exponential_distribution_negative_float_cpu(in
   float* p = static_cast<float*>(wholememory_tensor_get_data_pointer(output));
   wm::pcg32 rng;
   rng.init((uint64_t)random_seed, (uint64_t)subsequence);
-  for (int64_t i = 0; i < d.sizes[0]; ++i) p[i] = wm::key_from_weight<float>(1.0f, rng);
+  /* The reference's HOST replay is not the device formula: same draws, but the last step is double arithmetic,
+   * log1p(u) / log(2.0) rounded once to float (raft_random_gen.cu:85-117), where the device kernels compute
+   * log1pf(u) / logf(2.0) in float (func.cuh:45-63).  About a quarter of the values differ by one ulp, so the host
+   * function follows the host code (pinned by tests/test_ref_host_random.py against the reference source itself). */
+  for (int64_t i = 0; i < d.sizes[0]; ++i) {
+    float u = (float)(rng.next_u32() >> 8) / 16777216.0f;
+    u       = (float)-(0.5 + 0.5 * (double)u);
+    uint64_t r2 = 0;
+    int rounds  = -1;
+    do {
+      uint64_t lo = rng.next_u32();
+      uint64_t hi = rng.next_u32();
+      r2          = lo | (hi << 32);
+      ++rounds;
+    } while (r2 == 0);
+    const int one_bit = __builtin_clzll(r2) + rounds * 64;
+    u                 = (float)((double)u * pow(2.0, (double)-one_bit));
+    p[i]              = (float)(log1p((double)u) / log(2.0));
+  }
   return WHOLEMEMORY_SUCCESS;
 }
 
