@@ -1,0 +1,25 @@
+"""Differential test of the host-side descriptor / tensor-view logic against the REFERENCE SOURCE compiled for the CPU
+(oracle/_ref/ref_host_tensor.so = the reference's tensor_description.cpp + wholememory_tensor.cpp, built by
+oracle/build_ref_host_tensor.sh).  tests/cpp/host_diff_test.cpp drives both libraries with the same 200,000 randomised
+descriptors: dtype helpers, every create/copy/convert function, element counts and byte sizes, squeeze / unsqueeze,
+make_tensor_from_pointer (valid and refused descriptors), get_subtensor (-1 markers, empty, reversed and out-of-range
+windows: error code, resulting description, data pointer, root).  Zero divergences allowed.  CPU only."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "ref_host_tensor.so")
+OURS = os.path.join(ROOT, "wholegraph_b200", "lib", "libwholegraph.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/ref_host_tensor.so not built (needs /root/reference at build time)")
+def test_descriptor_and_view_logic_equals_the_reference_source(tmp_path):
+    exe = str(tmp_path / "host_diff_test")
+    p = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(ROOT, "tests", "cpp", "host_diff_test.cpp"), "-o", exe, "-ldl"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    p = subprocess.run([exe, OURS, REF_SO, "200000"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stderr.splitlines() if l.startswith("DIVERGENCE")]
+    assert p.returncode == 0 and "200000 iterations, 0 divergences" in p.stdout, "\n".join(lines[:20]) + "\n" + p.stdout[-500:]
