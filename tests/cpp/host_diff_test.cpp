@@ -10,6 +10,7 @@
  *   host_diff_test <ours.so> <reference_host.so> [iterations]        exit code = number of divergences (capped)
  */
 #include <wholememory/tensor_description.h>
+#include <wholememory/wholememory.h>
 #include <wholememory/wholememory_tensor.h>
 
 #include <dlfcn.h>
@@ -50,6 +51,7 @@ struct api {
   decltype(&wholememory_tensor_get_data_pointer) data_ptr;
   decltype(&wholememory_tensor_get_subtensor) subtensor;
   decltype(&wholememory_tensor_get_root) root;
+  decltype(&wholememory_create_tensor) create_tensor;
 };
 
 template <typename F>
@@ -81,7 +83,8 @@ bool load(const char* path, api* a)
          sym(a->so, "wholememory_unsqueeze_tensor", &a->unsqueeze) && sym(a->so, "wholememory_make_tensor_from_pointer", &a->from_ptr) &&
          sym(a->so, "wholememory_destroy_tensor", &a->destroy) && sym(a->so, "wholememory_tensor_has_handle", &a->has_handle) &&
          sym(a->so, "wholememory_tensor_get_tensor_description", &a->get_desc) && sym(a->so, "wholememory_tensor_get_data_pointer", &a->data_ptr) &&
-         sym(a->so, "wholememory_tensor_get_subtensor", &a->subtensor) && sym(a->so, "wholememory_tensor_get_root", &a->root);
+         sym(a->so, "wholememory_tensor_get_subtensor", &a->subtensor) && sym(a->so, "wholememory_tensor_get_root", &a->root) &&
+         sym(a->so, "wholememory_create_tensor", &a->create_tensor);
 }
 
 int g_div = 0;
@@ -261,6 +264,51 @@ int main(int argc, char** argv)
       if (t2) ref.destroy(t2);
     }
   }
-  printf("host_diff_test: %ld iterations, %d divergences\n", iters, g_div);
+  long create_cases = 0;
+  /* ---- wholememory_create_tensor: argument checks and the error code handed back when the allocation itself cannot
+   * succeed.  The communicator comes from this repo's library (the reference code only touches it through the C ABI);
+   * without a GPU every well-formed request ends in the same wholememory_malloc refusal on both sides, with a GPU the
+   * section is skipped (it would allocate). */
+  {
+    decltype(&wholememory_init) init_fn;
+    decltype(&wholememory_finalize) fini_fn;
+    decltype(&wholememory_create_unique_id) uid_fn;
+    decltype(&wholememory_create_communicator) comm_fn;
+    decltype(&wholememory_destroy_communicator) comm_free_fn;
+    decltype(&fork_get_device_count) devcount_fn;
+    if (sym(ours.so, "wholememory_init", &init_fn) && sym(ours.so, "wholememory_finalize", &fini_fn) &&
+        sym(ours.so, "wholememory_create_unique_id", &uid_fn) && sym(ours.so, "wholememory_create_communicator", &comm_fn) &&
+        sym(ours.so, "wholememory_destroy_communicator", &comm_free_fn) && sym(ours.so, "fork_get_device_count", &devcount_fn) &&
+        devcount_fn() == 0) {
+      init_fn(0, LEVEL_FATAL);
+      wholememory_unique_id_t uid;
+      wholememory_comm_t comm = nullptr;
+      if (uid_fn(&uid) == WHOLEMEMORY_SUCCESS && comm_fn(&comm, uid, 0, 1) == WHOLEMEMORY_SUCCESS) {
+        for (long it = 0; it < 4000; ++it) {
+          wholememory_tensor_description_t d;
+          ours.init_tensor(&d);
+          d.dim            = (int)pick(0, 3);
+          d.dtype          = (wholememory_dtype_t)pick(0, 9);
+          d.storage_offset = pick(0, 4) == 0 ? pick(1, 9) : 0;
+          d.sizes[0] = pick(1, 50), d.sizes[1] = pick(1, 20);
+          d.strides[1] = pick(0, 6) == 0 ? 2 : 1;
+          d.strides[0] = d.dim == 2 ? d.sizes[1] * d.strides[1] + pick(0, 3) : (pick(0, 6) == 0 ? 2 : 1);
+          auto mt  = (wholememory_memory_type_t)pick(1, 3);
+          auto loc = (wholememory_memory_location_t)pick(1, 2);
+          wholememory_tensor_t t1 = nullptr, t2 = nullptr;
+          wholememory_tensor_description_t d1 = d, d2 = d;
+          auto r1 = ours.create_tensor(&t1, &d1, comm, mt, loc, nullptr);
+          auto r2 = ref.create_tensor(&t2, &d2, comm, mt, loc, nullptr);
+          ++create_cases;
+          if ((int)r1 != (int)r2) diverge("create_tensor (code)", it, show(d) + " ours " + std::to_string((int)r1) + " reference " + std::to_string((int)r2));
+          if (r1 == WHOLEMEMORY_SUCCESS && t1) ours.destroy(t1);
+          if (r2 == WHOLEMEMORY_SUCCESS && t2) ref.destroy(t2);
+        }
+        comm_free_fn(comm);
+      }
+      fini_fn();
+    }
+  }
+  printf("host_diff_test: %ld iterations, %d divergences (%ld create_tensor cases)\n", iters, g_div, create_cases);
   return g_div > 100 ? 100 : g_div;
 }

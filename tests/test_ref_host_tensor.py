@@ -3,7 +3,8 @@
 oracle/build_ref_host_tensor.sh).  tests/cpp/host_diff_test.cpp drives both libraries with the same 200,000 randomised
 descriptors: dtype helpers, every create/copy/convert function, element counts and byte sizes, squeeze / unsqueeze,
 make_tensor_from_pointer (valid and refused descriptors), get_subtensor (-1 markers, empty, reversed and out-of-range
-windows: error code, resulting description, data pointer, root).  Zero divergences allowed.  CPU only."""
+windows: error code, resulting description, data pointer, root), and wholememory_create_tensor's argument checks (4,000
+descriptors x memory type x location on a single-rank communicator).  Zero divergences allowed.  CPU only."""
 import os
 import subprocess
 
@@ -22,4 +23,5 @@ def test_descriptor_and_view_logic_equals_the_reference_source(tmp_path):
     assert p.returncode == 0, p.stderr[-3000:]
     p = subprocess.run([exe, OURS, REF_SO, "200000"], capture_output=True, text=True, timeout=600)
     lines = [l for l in p.stderr.splitlines() if l.startswith("DIVERGENCE")]
+    assert "(4000 create_tensor cases)" in p.stdout or "(0 create_tensor cases)" in p.stdout, p.stdout[-300:]  # 0 only on a GPU box
     assert p.returncode == 0 and "200000 iterations, 0 divergences" in p.stdout, "\n".join(lines[:20]) + "\n" + p.stdout[-500:]
