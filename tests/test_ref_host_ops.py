@@ -1,0 +1,27 @@
+"""Argument checks of wholememory_gather / wholememory_scatter against the REFERENCE SOURCE compiled for the CPU
+(oracle/_ref/ref_host_ops.so = the reference's gather_op.cpp + scatter_op.cpp + tensor code, GPU dispatch targets stubbed;
+built by oracle/build_ref_host_ops.sh).  tests/cpp/ops_validation_diff.cpp sends 100,000 operand triples -- well-formed
+ones, rank / width / dtype mismatches, and descriptions corrupted after creation -- through both libraries: wherever the
+reference refuses, this library must refuse with the same error code; wherever the reference dispatches, this library
+must get as far as its kernel launch (which, on this GPU-less machine, is the loud "no CPU fallback" CUDA error).
+One documented superset is exempt: a 1-D dense operand for a 1-D table.  CPU only; on a GPU box the program compares nothing."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "ref_host_ops.so")
+OURS = os.path.join(ROOT, "wholegraph_b200", "lib", "libwholegraph.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/ref_host_ops.so not built (needs /root/reference at build time)")
+def test_gather_scatter_argument_checks_equal_the_reference_source(tmp_path):
+    exe = str(tmp_path / "ops_validation_diff")
+    p = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(ROOT, "tests", "cpp", "ops_validation_diff.cpp"), "-o", exe, "-ldl"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    p = subprocess.run([exe, OURS, REF_SO, "100000"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stderr.splitlines() if l.startswith("DIVERGENCE")]
+    ok = "100000 iterations, 0 divergences" in p.stdout or "a GPU is present" in p.stdout
+    assert p.returncode == 0 and ok, "\n".join(lines[:20]) + "\n" + p.stdout[-500:]

@@ -88,31 +88,38 @@ struct op_args {
   void* dense_ptr;
 };
 
-/* shared descriptor checks; `what` names the dense operand for messages */
+/* Shared descriptor checks, in the reference's order and with its error codes (gather_op.cpp:38-82, scatter_op.cpp:38-79;
+ * pinned by tests/cpp/ops_validation_diff.cpp against those files compiled for the CPU).  `what` names the dense operand.
+ * Two quirks of the reference are kept on purpose:
+ *  - a 1-D table is unsqueezed to [N, 1] BEFORE the rank comparison, so the dense operand it expects for a 1-D table is
+ *    the 2-D [n, 1] one.  (A 1-D dense operand for a 1-D table, which the reference refuses, is accepted here as well.)
+ *  - a table that cannot be viewed as a matrix is WHOLEMEMORY_LOGIC_ERROR for gather but WHOLEMEMORY_INVALID_INPUT for scatter. */
 wholememory_error_code_t prepare(wholememory_tensor_t table,
                                  wholememory_tensor_t indices,
                                  wholememory_tensor_t dense,
                                  const char* what,
+                                 bool is_gather,
                                  op_args* a)
 {
   if (table == nullptr || indices == nullptr || dense == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  const wholememory_error_code_t bad_table = is_gather ? WHOLEMEMORY_LOGIC_ERROR : WHOLEMEMORY_INVALID_INPUT;
   wholememory_tensor_description_t td = *wholememory_tensor_get_tensor_description(table);
   if (td.dim != 1 && td.dim != 2) {
     WM_ERROR("wholememory_tensor should be 1D or 2D tensor.");
     return WHOLEMEMORY_INVALID_INPUT;
   }
   const int table_dim = td.dim;
-  if (td.dim == 1 && !wholememory_unsqueeze_tensor(&td, 1)) return WHOLEMEMORY_LOGIC_ERROR;
+  if (td.dim == 1 && !wholememory_unsqueeze_tensor(&td, 1)) return bad_table;
   if (!wholememory_convert_tensor_desc_to_matrix(&a->table, &td)) {
     WM_ERROR("wholememory_tensor cannot be viewed as a matrix.");
-    return WHOLEMEMORY_LOGIC_ERROR;
+    return bad_table;
   }
   if (wholememory_tensor_get_tensor_description(indices)->dim != 1) {
     WM_ERROR("indices tensor should be 1D tensor");
     return WHOLEMEMORY_INVALID_INPUT;
   }
   wholememory_tensor_description_t dd = *wholememory_tensor_get_tensor_description(dense);
-  if (dd.dim != table_dim) {
+  if (dd.dim != 2 && !(dd.dim == 1 && table_dim == 1)) {
     WM_ERROR("%s tensor should be same dim as wholememory_tensor.", what);
     return WHOLEMEMORY_INVALID_INPUT;
   }
@@ -148,7 +155,7 @@ wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_ten
 {
   return wm::guarded("wholememory_gather", [&]() -> wholememory_error_code_t {
     wm::op_args a;
-    auto rc = wm::prepare(wholememory_tensor, indices_tensor, output_tensor, "output", &a);
+    auto rc = wm::prepare(wholememory_tensor, indices_tensor, output_tensor, "output", true, &a);
     if (rc != WHOLEMEMORY_SUCCESS) return rc;
     auto s = static_cast<cudaStream_t>(stream);
     if (wholememory_tensor->is_wm && !wm::handle_is_addressable(wholememory_tensor->handle)) {
@@ -169,7 +176,7 @@ wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor,
 {
   return wm::guarded("wholememory_scatter", [&]() -> wholememory_error_code_t {
     wm::op_args a;
-    auto rc = wm::prepare(wholememory_tensor, indices_tensor, input_tensor, "input", &a);
+    auto rc = wm::prepare(wholememory_tensor, indices_tensor, input_tensor, "input", false, &a);
     if (rc != WHOLEMEMORY_SUCCESS) return rc;
     auto s = static_cast<cudaStream_t>(stream);
     if (wholememory_tensor->is_wm && !wm::handle_is_addressable(wholememory_tensor->handle)) {
