@@ -10,6 +10,7 @@
  * (T + first neighbor position); a neighbor is "new" iff that minimum is its own T + position; an exclusive scan of the
  * new-flags gives the final ids.  One host sync (the output size), as the allocation callback ABI requires.
  */
+#include "ops_internal.hpp"
 #include "wm_internal.hpp"
 
 #include <cub/device/device_scan.cuh>
@@ -169,33 +170,53 @@ wholememory_error_code_t graph_append_unique(wholememory_tensor_t target_nodes_t
 {
   return wm::guarded("graph_append_unique", [&]() -> wholememory_error_code_t {
     using namespace wm;
-    if (!target_nodes_tensor || !neighbor_nodes_tensor || !output_unique_node_memory_context || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
-    auto td = *wholememory_tensor_get_tensor_description(target_nodes_tensor);
-    auto nd = *wholememory_tensor_get_tensor_description(neighbor_nodes_tensor);
-    if (td.dim != 1 || nd.dim != 1) {
-      WM_ERROR("target_nodes_tensor and neighbor_nodes_tensor should be 1D tensors.");
+    if (!target_nodes_tensor || !neighbor_nodes_tensor) return WHOLEMEMORY_INVALID_INPUT;
+    /* argument checks in the reference's order and with its codes (graph_ops/append_unique.cpp:28-72) ... */
+    if (!is_1d(target_nodes_tensor)) {
+      WM_ERROR("target_nodes_tensor should be 1D tensor.");
       return WHOLEMEMORY_INVALID_INPUT;
     }
-    if (td.dtype != nd.dtype || (td.dtype != WHOLEMEMORY_DT_INT && td.dtype != WHOLEMEMORY_DT_INT64)) {
-      WM_ERROR("target / neighbor nodes must share an int32 or int64 dtype.");
+    if (!is_1d(neighbor_nodes_tensor)) {
+      WM_ERROR("neighbor_nodes_tensor should be 1D tensor.");
       return WHOLEMEMORY_INVALID_INPUT;
     }
     int* mapping = nullptr;
-    if (output_neighbor_raw_to_unique_mapping_tensor != nullptr) {
+    bool want_mapping = false;
+    if (output_neighbor_raw_to_unique_mapping_tensor != nullptr) { /* the reference requires a tensor object; "None" is a 0-dim one */
       auto md = *wholememory_tensor_get_tensor_description(output_neighbor_raw_to_unique_mapping_tensor);
       if (md.dim != 1 && md.dim != 0) {
         WM_ERROR("output_neighbor_raw_to_unique_mapping_tensor should be 1D tensor or None.");
         return WHOLEMEMORY_INVALID_INPUT;
       }
-      if (md.dim == 1) {
-        if (md.dtype != WHOLEMEMORY_DT_INT || md.sizes[0] != nd.sizes[0]) {
-          WM_ERROR("output_neighbor_raw_to_unique_mapping_tensor should be an int tensor with one entry per neighbor.");
-          return WHOLEMEMORY_INVALID_INPUT;
-        }
-        mapping = static_cast<int*>(wholememory_tensor_get_data_pointer(output_neighbor_raw_to_unique_mapping_tensor));
+      if (md.dim == 1 && md.dtype != WHOLEMEMORY_DT_INT) {
+        WM_ERROR("output_neighbor_raw_to_unique_mapping_tensor should be int tensor or None.");
+        return WHOLEMEMORY_INVALID_INPUT;
       }
+      want_mapping = md.dim == 1;
     }
+    if (!views_as_array(target_nodes_tensor) || !views_as_array(neighbor_nodes_tensor)) {
+      WM_ERROR("Input target_nodes_tensor / neighbor_nodes_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    auto td = *wholememory_tensor_get_tensor_description(target_nodes_tensor);
+    auto nd = *wholememory_tensor_get_tensor_description(neighbor_nodes_tensor);
+    if (td.dtype != nd.dtype) {
+      WM_ERROR("target_nodes_dtype should be the same with neighbor_nodes_dtype");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    /* ... then the point where the reference dispatches to its GPU translation unit, whose failures are all LOGIC_ERROR
+     * (append_unique_impl.cu:36-56) */
     require_cuda("graph_append_unique");
+    WM_EXPECT(output_unique_node_memory_context != nullptr && p_env_fns != nullptr, WHOLEMEMORY_INVALID_INPUT,
+              "graph_append_unique needs an output memory context and env functions");
+    WM_EXPECT(td.dtype == WHOLEMEMORY_DT_INT || td.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR,
+              "target / neighbor nodes must be int32 or int64");
+    if (want_mapping) {
+      auto md = *wholememory_tensor_get_tensor_description(output_neighbor_raw_to_unique_mapping_tensor);
+      WM_EXPECT(md.sizes[0] == nd.sizes[0], WHOLEMEMORY_INVALID_INPUT,
+                "output_neighbor_raw_to_unique_mapping_tensor should have one entry per neighbor");
+      mapping = static_cast<int*>(wholememory_tensor_get_data_pointer(output_neighbor_raw_to_unique_mapping_tensor));
+    }
     WM_EXPECT(td.sizes[0] + nd.sizes[0] < ((int64_t)1 << 30), WHOLEMEMORY_INVALID_VALUE, "too many nodes for append_unique");
     const void* tg = wholememory_tensor_get_data_pointer(target_nodes_tensor);
     const void* nb = wholememory_tensor_get_data_pointer(neighbor_nodes_tensor);
@@ -217,14 +238,24 @@ wholememory_error_code_t csr_add_self_loop(wholememory_tensor_t csr_row_ptr_tens
   return wm::guarded("csr_add_self_loop", [&]() -> wholememory_error_code_t {
     using namespace wm;
     wholememory_tensor_t ts[4] = {csr_row_ptr_tensor, csr_col_ptr_tensor, output_csr_row_ptr_tensor, output_csr_col_ptr_tensor};
-    for (auto t : ts) {
+    for (auto t : ts)
       if (t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    /* argument checks in the reference's order and with its codes (graph_ops/csr_add_self_loop.cpp:26-87): rank and dtype
+     * of each tensor in turn (INVALID_INPUT), then "views as an array" for each (LOGIC_ERROR) ... */
+    for (auto t : ts) {
       auto* d = wholememory_tensor_get_tensor_description(t);
-      if (d->dim != 1 || d->dtype != WHOLEMEMORY_DT_INT) { /* reference csr_add_self_loop.cpp:28-62 */
+      if (d->dim != 1 || d->dtype != WHOLEMEMORY_DT_INT) {
         WM_ERROR("csr_add_self_loop: all four tensors should be 1D int tensors.");
         return WHOLEMEMORY_INVALID_INPUT;
       }
     }
+    for (auto t : ts)
+      if (!views_as_array(t)) {
+        WM_ERROR("csr_add_self_loop: tensor convert to array failed.");
+        return WHOLEMEMORY_LOGIC_ERROR;
+      }
+    /* ... then the point where the reference dispatches to its GPU translation unit */
+    require_cuda("csr_add_self_loop");
     auto* rd = wholememory_tensor_get_tensor_description(csr_row_ptr_tensor);
     auto* cd = wholememory_tensor_get_tensor_description(csr_col_ptr_tensor);
     auto* od = wholememory_tensor_get_tensor_description(output_csr_row_ptr_tensor);
@@ -234,7 +265,6 @@ wholememory_error_code_t csr_add_self_loop(wholememory_tensor_t csr_row_ptr_tens
       WM_ERROR("csr_add_self_loop: output sizes must be rows+1 and edges+rows.");
       return WHOLEMEMORY_INVALID_INPUT;
     }
-    require_cuda("csr_add_self_loop");
     if (rows <= 0) return WHOLEMEMORY_SUCCESS;
     add_self_loop_kernel<<<(unsigned)rows, 64, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const int*>(wholememory_tensor_get_data_pointer(csr_row_ptr_tensor)),

@@ -309,15 +309,41 @@ wholememory_error_code_t wholegraph_csr_unweighted_sample_without_replacement(wh
     using namespace wm;
     if (!wm_csr_row_ptr_tensor || !wm_csr_col_ptr_tensor || !center_nodes_tensor || !output_sample_offset_tensor)
       return WHOLEMEMORY_INVALID_INPUT;
+    /* argument checks in the reference's order and with its codes (unweighted_sample_without_replacement.cpp:64-111) ... */
+    if (!is_1d(wm_csr_row_ptr_tensor)) {
+      WM_ERROR("wm_csr_row_ptr_tensor should be 1D tensor.");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!is_1d(wm_csr_col_ptr_tensor)) {
+      WM_ERROR("wm_csr_col_ptr_tensor should be 1D tensor.");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!views_as_array(wm_csr_row_ptr_tensor) || !views_as_array(wm_csr_col_ptr_tensor)) {
+      WM_ERROR("Input wm_csr_row_ptr_tensor / wm_csr_col_ptr_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    if (!is_1d(center_nodes_tensor)) {
+      WM_ERROR("Input center_nodes_tensor should be 1D tensor");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!views_as_array(center_nodes_tensor)) {
+      WM_ERROR("Input center_nodes_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    if (!is_1d(output_sample_offset_tensor)) {
+      WM_ERROR("Output output_sample_offset_tensor should be 1D tensor.");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!views_as_array(output_sample_offset_tensor)) {
+      WM_ERROR("Output output_sample_offset_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    /* ... then the point where the reference dispatches to its GPU translation unit */
     require_cuda("neighbor sampling");
     auto rd = *wholememory_tensor_get_tensor_description(wm_csr_row_ptr_tensor);
     auto cd = *wholememory_tensor_get_tensor_description(wm_csr_col_ptr_tensor);
     auto nd = *wholememory_tensor_get_tensor_description(center_nodes_tensor);
     auto od = *wholememory_tensor_get_tensor_description(output_sample_offset_tensor);
-    if (rd.dim != 1 || cd.dim != 1 || nd.dim != 1 || od.dim != 1) {
-      WM_ERROR("row_ptr, col_ptr, center_nodes and output_sample_offset must be 1D tensors.");
-      return WHOLEMEMORY_INVALID_INPUT;
-    }
     /* dtype rules: reference unweighted_sample_without_replacement_func.cuh:304-315 */
     WM_EXPECT(rd.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR, "wm_csr_row_ptr dtype must be int64, got %d", (int)rd.dtype);
     WM_EXPECT(od.dtype == WHOLEMEMORY_DT_INT, WHOLEMEMORY_LOGIC_ERROR, "output_sample_offset dtype must be int32, got %d", (int)od.dtype);

@@ -43,4 +43,16 @@ cvt_launch_fn find_float_cvt(wholememory_dtype_t table_dt, wholememory_dtype_t d
 cvt_launch_fn find_int_cvt(wholememory_dtype_t table_dt, wholememory_dtype_t dense_dt);
 int cvt_blocks_per_sm();
 
+/* The two checks every 1-D operand of the graph / sampling entry points goes through in the reference, with its codes:
+ * rank != 1 -> WHOLEMEMORY_INVALID_INPUT, then "cannot be viewed as an array" (last stride != 1, unknown dtype) ->
+ * WHOLEMEMORY_LOGIC_ERROR (e.g. unweighted_sample_without_replacement.cpp:64-111).  The call order at each entry point
+ * follows the reference's too; tests/cpp/graph_validation_diff.cpp compares it with the reference source on CPU. */
+inline bool is_1d(wholememory_tensor_t t) { return wholememory_tensor_get_tensor_description(t)->dim == 1; }
+inline bool views_as_array(wholememory_tensor_t t)
+{
+  wholememory_array_description_t a;
+  wholememory_tensor_description_t d = *wholememory_tensor_get_tensor_description(t);
+  return wholememory_convert_tensor_desc_to_array(&a, &d);
+}
+
 }  // namespace wm

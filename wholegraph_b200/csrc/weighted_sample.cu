@@ -324,15 +324,40 @@ wholememory_error_code_t wholegraph_csr_weighted_sample_without_replacement(whol
     if (!wm_csr_row_ptr_tensor || !wm_csr_col_ptr_tensor || !wm_csr_weight_ptr_tensor || !center_nodes_tensor ||
         !output_sample_offset_tensor)
       return WHOLEMEMORY_INVALID_INPUT;
+    /* argument checks in the reference's order and with its codes (weighted_sample_without_replacement.cpp:74-126) ... */
+    for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor})
+      if (!is_1d(t)) {
+        WM_ERROR("wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor and wm_csr_weight_ptr_tensor should be 1D tensors.");
+        return WHOLEMEMORY_INVALID_INPUT;
+      }
+    for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor})
+      if (!views_as_array(t)) {
+        WM_ERROR("Input CSR tensor convert to array failed.");
+        return WHOLEMEMORY_LOGIC_ERROR;
+      }
+    if (!is_1d(center_nodes_tensor)) {
+      WM_ERROR("Input center_nodes_tensor should be 1D tensor");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!views_as_array(center_nodes_tensor)) {
+      WM_ERROR("Input center_nodes_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    if (!is_1d(output_sample_offset_tensor)) {
+      WM_ERROR("Output output_sample_offset_tensor should be 1D tensor.");
+      return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (!views_as_array(output_sample_offset_tensor)) {
+      WM_ERROR("Output output_sample_offset_tensor convert to array failed.");
+      return WHOLEMEMORY_LOGIC_ERROR;
+    }
+    /* ... then the point where the reference dispatches to its GPU translation unit */
+    require_cuda("weighted neighbor sampling");
     auto rd = *wholememory_tensor_get_tensor_description(wm_csr_row_ptr_tensor);
     auto cd = *wholememory_tensor_get_tensor_description(wm_csr_col_ptr_tensor);
     auto wd = *wholememory_tensor_get_tensor_description(wm_csr_weight_ptr_tensor);
     auto nd = *wholememory_tensor_get_tensor_description(center_nodes_tensor);
     auto od = *wholememory_tensor_get_tensor_description(output_sample_offset_tensor);
-    if (rd.dim != 1 || cd.dim != 1 || wd.dim != 1 || nd.dim != 1 || od.dim != 1) {
-      WM_ERROR("row_ptr, col_ptr, weight_ptr, center_nodes and output_sample_offset must be 1D tensors.");
-      return WHOLEMEMORY_INVALID_INPUT;
-    }
     WM_EXPECT(rd.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR, "wm_csr_row_ptr dtype must be int64");
     WM_EXPECT(od.dtype == WHOLEMEMORY_DT_INT, WHOLEMEMORY_LOGIC_ERROR, "output_sample_offset dtype must be int32");
     WM_EXPECT(cd.dtype == WHOLEMEMORY_DT_INT || cd.dtype == WHOLEMEMORY_DT_INT64, WHOLEMEMORY_LOGIC_ERROR, "col dtype must be int32/int64");
@@ -341,7 +366,6 @@ wholememory_error_code_t wholegraph_csr_weighted_sample_without_replacement(whol
     WM_EXPECT(wd.sizes[0] == cd.sizes[0], WHOLEMEMORY_INVALID_INPUT, "one weight per edge expected");
     WM_EXPECT(od.sizes[0] == nd.sizes[0] + 1, WHOLEMEMORY_INVALID_INPUT, "output_sample_offset must have center_count + 1 entries");
     WM_EXPECT(nd.sizes[0] < ((int64_t)1 << 31) - 1, WHOLEMEMORY_INVALID_VALUE, "too many center nodes");
-    require_cuda("weighted neighbor sampling");
     for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor})
       WM_EXPECT(!t->is_wm || handle_is_addressable(t->handle), WHOLEMEMORY_NOT_IMPLEMENTED,
                 "weighted sampling needs peer-addressable CSR memory (no bucket-exchange variant; the reference has none either)");
