@@ -1,0 +1,168 @@
+"""The ctypes binding (wholegraph_b200/binding.py) against the reference's OWN cython module, which oracle/build_ref_binding.sh
+compiles unmodified and links to this repo's library (oracle/_ref/refbinding).  Both import on a CPU box, so the comparison
+runs here:
+  * every public name of the reference module exists in this binding; enums have the same members and values; classes have
+    the same public methods;
+  * GlobalContextWrapper: the same Python callbacks registered through both modules are invoked with the same arguments, in
+    the same order, when the library drives the env-function table (temporary and output protocol, HOST allocations)."""
+import ctypes
+import enum
+import glob
+import os
+import sys
+
+import pytest
+import torch
+
+import wholegraph_b200.binding as wmb
+from wholegraph_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIND_DIR = os.path.join(ROOT, "oracle", "_ref", "refbinding")
+
+pytestmark = pytest.mark.skipif(not glob.glob(os.path.join(BIND_DIR, "wholememory_binding*.so")),
+                                reason="oracle/_ref/refbinding not built (needs /root/reference + cython at build time)")
+
+_KEEP = []  # the reference wrapper's __dealloc__ is broken (pyx:387-397 dereferences self.self): never collect it
+
+
+@pytest.fixture(scope="module")
+def rwmb():
+    sys.path.insert(0, BIND_DIR)
+    import wholememory_binding as m
+    return m
+
+
+def test_public_names_enums_and_methods(rwmb):
+    public = [n for n in dir(rwmb) if not n.startswith("_") and n not in ("array", "functools")]  # two stray imports
+    assert [n for n in public if not hasattr(wmb, n)] == []
+    for n in public:
+        theirs, ours = getattr(rwmb, n), getattr(wmb, n)
+        if isinstance(theirs, type) and issubclass(theirs, enum.Enum):
+            mine = {m.name: int(m.value) for m in ours}
+            for m in theirs:
+                assert mine.get(m.name) == int(m.value), (n, m.name)
+                assert int(getattr(wmb, m.name)) == int(m.value)  # cpdef enums are also module-level constants
+        elif isinstance(theirs, type):
+            missing = [m for m in dir(theirs) if not m.startswith("_") and not hasattr(ours, m)]
+            assert missing == [], (n, missing)
+
+
+class _Ctx(object):
+    def __init__(self, tag):
+        self.tag = tag
+        self.tensor = None
+
+
+def _drive(module, log):
+    """Register logging callbacks through `module`, then drive the resulting C table the way the library does."""
+    counter = [0]
+
+    def create(global_context):
+        counter[0] += 1
+        log.append(("create", global_context))
+        return _Ctx("temp%d" % counter[0])
+
+    def destroy(memory_context, global_context):
+        log.append(("destroy", memory_context.tag, global_context))
+
+    def malloc(desc, malloc_type, memory_context, global_context):
+        log.append(("malloc", tuple(desc.shape), int(desc.dtype), int(malloc_type.get_type()), memory_context.tag, global_context))
+        memory_context.tensor = torch.zeros(tuple(desc.shape), dtype=torch.int64 if int(desc.dtype) == 6 else torch.float32)
+        return memory_context.tensor.data_ptr()
+
+    def free(memory_context, global_context):
+        log.append(("free", memory_context.tag, global_context))
+        memory_context.tensor = None
+
+    wrapper = module.GlobalContextWrapper()
+    wrapper.create_context(create, destroy, malloc, free, "TEMP-GLOBAL", malloc, free, "OUT-GLOBAL")
+    _KEEP.append(wrapper)
+    ctypes.pythonapi.Py_IncRef(ctypes.py_object(wrapper))
+    env = ctypes.cast(wrapper.get_env_fns(), ctypes.POINTER(_lib.EnvFns)).contents
+    t, o = env.temporary_fns, env.output_fns
+
+    def desc(shape, dtype):
+        d = _lib.TensorDescription()
+        for i, s in enumerate(shape):
+            d.sizes[i], d.strides[i] = s, 1
+        d.dim, d.dtype, d.storage_offset = len(shape), dtype, 0
+        return d
+
+    ctx = ctypes.c_void_p()
+    t.create_memory_context_fn(ctypes.byref(ctx), t.global_context)
+    d = desc((6,), 6)
+    p1 = t.malloc_fn(ctypes.byref(d), 2, ctx, t.global_context)  # HOST
+    assert p1
+    ctypes.memset(p1, 0, 48)
+    t.free_fn(ctx, t.global_context)
+    t.destroy_memory_context_fn(ctx, t.global_context)
+    out_ctx = _Ctx("caller-owned")
+    d = desc((3, 5), 1)
+    p2 = o.malloc_fn(ctypes.byref(d), 2, id(out_ctx), o.global_context)
+    assert p2 == out_ctx.tensor.data_ptr() and tuple(out_ctx.tensor.shape) == (3, 5)
+    o.free_fn(id(out_ctx), o.global_context)
+    assert out_ctx.tensor is None
+
+
+def test_global_context_wrapper_protocol_matches_the_reference_module(rwmb):
+    theirs, ours = [], []
+    _drive(rwmb, theirs)
+    _drive(wmb, ours)
+    assert ours == theirs
+    assert [e[0] for e in ours] == ["create", "malloc", "free", "destroy", "malloc", "free"]
+
+
+def test_view_getters_accept_both_call_forms():
+    """This binding's (dtype, location, device) form and the reference's (import_dlpack_fn, dtype, location, device) form
+    (pyx:1368-1412, :1612-1650) reach the same view; the importer, when given, is applied to it."""
+
+    class FakeHandle(wmb.PyWholeMemoryHandle):
+        def _local_flat(self, dtype, loc, dev):
+            return torch.arange(12, dtype=torch.float32), 4
+
+        def _global_flat(self, dtype, loc, dev):
+            return torch.arange(24, dtype=torch.float32), 0
+
+        def _chunked_flat(self, dtype, loc, dev):
+            return [torch.arange(12, dtype=torch.float32), torch.arange(12, 24, dtype=torch.float32)], [0, 12]
+
+    h = FakeHandle()
+    seen = []
+
+    def importer(t):
+        seen.append(tuple(t.shape))
+        return torch.utils.dlpack.from_dlpack(t.__dlpack__())
+
+    args = (wmb.DtFloat, wmb.MlHost, -1)
+    a, off = h.get_local_flatten_tensor(*args)
+    b, off2 = h.get_local_flatten_tensor(importer, *args)
+    assert torch.equal(a, b) and off == off2 == 4 and seen == [(12,)]
+    a, _ = h.get_global_flatten_tensor(*args)
+    b, _ = h.get_global_flatten_tensor(importer, *args)
+    assert torch.equal(a, b)
+    (a0, a1), offs = h.get_all_chunked_flatten_tensor(*args)
+    (b0, b1), offs2 = h.get_all_chunked_flatten_tensor(importer, *args)
+    assert torch.equal(a0, b0) and torch.equal(a1, b1) and offs == offs2 == [0, 12]
+    with pytest.raises(TypeError):
+        h.get_local_flatten_tensor(wmb.DtFloat, wmb.MlHost)
+
+    class FakeTensor(wmb.PyWholeMemoryTensor):
+        def get_wholememory_handle(self):
+            return h
+
+        @property
+        def dtype(self):
+            return wmb.DtFloat
+
+        def get_tensor_in_window(self, flat, off):
+            return flat, off
+
+    t = FakeTensor()
+    x, off = t.get_local_tensor(wmb.MlHost, -1)
+    y, off2 = t.get_local_tensor(importer, wmb.MlHost, -1)
+    assert torch.equal(x, y) and off == off2 == 4
+    assert torch.equal(t.get_global_tensor(wmb.MlHost, -1), t.get_global_tensor(importer, wmb.MlHost, -1))
+    (c0, c1), coffs = t.get_all_chunked_tensor(wmb.MlHost, -1)
+    (d0, d1), doffs = t.get_all_chunked_tensor(importer, wmb.MlHost, -1)
+    assert torch.equal(c0, d0) and torch.equal(c1, d1) and coffs == doffs

@@ -103,8 +103,8 @@ for _e in (WholeMemoryErrorCode, WholeMemoryMemoryType, WholeMemoryMemoryLocatio
            WholeMemoryLogLevel, WholeMemoryMemoryAllocType, WholeMemoryDataType, WholeMemoryAccessType,
            WholeMemoryOptimizerType, WholeMemoryViewType):
     for _m in _e:
-        if _m.name not in ("NotImplemented", "SystemError"):
-            globals()[_m.name] = _m
+        if _m.name != "SystemError":  # not a member of the reference's enum; keep the builtin exception type visible
+            globals()[_m.name] = _m   # incl. `NotImplemented` = 2, which the reference module exports as well
 
 
 def check_wholememory_error_code(err):
@@ -313,6 +313,18 @@ class PyWholeMemoryHandle:
         _chk(lib.wholememory_get_communicator(byref(comm), self.wholememory_handle))
         return PyWholeMemoryComm(comm.value)
 
+    def get_local_communicator(self):
+        """HIERARCHY memory only: this build answers WHOLEMEMORY_NOT_SUPPORTED (NotImplementedError)."""
+        comm = c_void_p()
+        _chk(lib.wholememory_get_local_communicator(byref(comm), self.wholememory_handle))
+        return PyWholeMemoryComm(comm.value)
+
+    def get_cross_communicator(self):
+        """HIERARCHY memory only: this build answers WHOLEMEMORY_NOT_SUPPORTED (NotImplementedError)."""
+        comm = c_void_p()
+        _chk(lib.wholememory_get_cross_communicator(byref(comm), self.wholememory_handle))
+        return PyWholeMemoryComm(comm.value)
+
     def get_memory_type(self):
         return WholeMemoryMemoryType(lib.wholememory_get_memory_type(self.wholememory_handle))
 
@@ -348,18 +360,35 @@ class PyWholeMemoryHandle:
         _chk(lib.wholememory_get_rank_partition_offsets(arr, self.wholememory_handle))
         return list(arr)
 
-    # torch views (reference: get_local_flatten_tensor / get_global_flatten_tensor / get_all_chunked_flatten_tensor)
-    def get_local_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+    # torch views (reference: get_local_flatten_tensor / get_global_flatten_tensor / get_all_chunked_flatten_tensor).
+    # Both call forms are accepted: this binding's (dtype, location, device id) and the reference's, whose first argument
+    # is the DLPack importer (pyx:1368-1412); the importer is then applied to the view (torch tensors speak __dlpack__).
+    def get_local_flatten_tensor(self, *args):
+        fn, (dtype, view_from_location, view_from_device_id) = _split_importer(args)
+        t, off = self._local_flat(dtype, view_from_location, view_from_device_id)
+        return (fn(t) if fn else t), off
+
+    def get_global_flatten_tensor(self, *args):
+        fn, (dtype, view_from_location, view_from_device_id) = _split_importer(args)
+        t, off = self._global_flat(dtype, view_from_location, view_from_device_id)
+        return (fn(t) if fn else t), off
+
+    def get_all_chunked_flatten_tensor(self, *args):
+        fn, (dtype, view_from_location, view_from_device_id) = _split_importer(args)
+        ts, offs = self._chunked_flat(dtype, view_from_location, view_from_device_id)
+        return ([fn(t) for t in ts] if fn else ts), offs
+
+    def _local_flat(self, dtype, view_from_location, view_from_device_id):
         p, s, o = self.get_local_memory()
         es = lib.wholememory_dtype_get_element_size(int(dtype))
         return _view_as_torch(p, s, dtype, self._view_loc(view_from_location), view_from_device_id, self), o // es
 
-    def get_global_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+    def _global_flat(self, dtype, view_from_location, view_from_device_id):
         p = self.get_global_pointer()
         return _view_as_torch(p, self.get_total_size(), dtype, self._view_loc(view_from_location),
                               view_from_device_id, self), 0
 
-    def get_all_chunked_flatten_tensor(self, dtype, view_from_location, view_from_device_id):
+    def _chunked_flat(self, dtype, view_from_location, view_from_device_id):
         n = self.get_communicator().get_size()
         es = lib.wholememory_dtype_get_element_size(int(dtype))
         tensors, offsets = [], []
@@ -377,13 +406,34 @@ class PyWholeMemoryHandle:
         return view
 
     def from_filelist(self, memory_offset, memory_entry_size, file_entry_size, round_robin_size, file_list):
-        arr = (ctypes.c_char_p * len(file_list))(*[f.encode() for f in file_list])
-        _chk(lib.wholememory_load_from_file(self.wholememory_handle, memory_offset, memory_entry_size, file_entry_size,
-                                            arr, len(file_list), round_robin_size))
+        load_wholememory_handle_from_filelist(self.wholememory_handle.value, memory_offset, memory_entry_size, file_entry_size,
+                                              round_robin_size, file_list)
 
     def to_file(self, memory_offset, memory_entry_size, file_entry_size, file_name):
-        _chk(lib.wholememory_store_to_file(self.wholememory_handle, memory_offset, memory_entry_size, file_entry_size,
-                                           file_name.encode()))
+        store_wholememory_handle_to_file(self.wholememory_handle.value, memory_offset, memory_entry_size, file_entry_size, file_name)
+
+
+def _split_importer(args):
+    """(import_dlpack_fn or None, the remaining three view arguments)"""
+    if len(args) == 4 and callable(args[0]):
+        return args[0], args[1:]
+    if len(args) != 3:
+        raise TypeError("expected ([import_dlpack_fn,] dtype, view_from_location, view_from_device_id)")
+    return None, args
+
+
+def load_wholememory_handle_from_filelist(wholememory_handle_int_ptr, memory_offset, memory_entry_size, file_entry_size,
+                                          round_robin_size, file_list):
+    """Every rank loads its partition from the list of raw binary files (reference pyx:1836-1861)."""
+    arr = (ctypes.c_char_p * len(file_list))(*[f.encode() for f in file_list])
+    _chk(lib.wholememory_load_from_file(c_void_p(wholememory_handle_int_ptr), memory_offset, memory_entry_size, file_entry_size,
+                                        arr, len(file_list), round_robin_size))
+
+
+def store_wholememory_handle_to_file(wholememory_handle_int_ptr, memory_offset, memory_entry_size, file_entry_size, file_name):
+    """Every rank stores its partition to its own file (reference pyx:1863-1873)."""
+    _chk(lib.wholememory_store_to_file(c_void_p(wholememory_handle_int_ptr), memory_offset, memory_entry_size, file_entry_size,
+                                       file_name.encode()))
 
 
 class PyWholeMemoryTensorDescription:
@@ -523,19 +573,23 @@ class PyWholeMemoryTensor:
         return (mat[start_indice0:end_indice0, storage_offset1:storage_offset1 + d.sizes[1]],
                 max(0, vector_start_offset - storage_offset0))
 
-    def get_local_tensor(self, view_from_location, view_from_device_id):
-        flat, off = self.get_wholememory_handle().get_local_flatten_tensor(self.dtype, view_from_location,
-                                                                           view_from_device_id)
+    # like the handle's getters, these also take the reference's form with the DLPack importer first (pyx:1612-1650)
+    def get_local_tensor(self, *args):
+        fn, (view_from_location, view_from_device_id) = _split_importer2(args)
+        flat, off = self.get_wholememory_handle().get_local_flatten_tensor(*_with_importer(fn, self.dtype, view_from_location,
+                                                                                           view_from_device_id))
         return self.get_tensor_in_window(flat, off)
 
-    def get_global_tensor(self, view_from_location, view_from_device_id):
-        flat, _ = self.get_wholememory_handle().get_global_flatten_tensor(self.dtype, view_from_location,
-                                                                          view_from_device_id)
+    def get_global_tensor(self, *args):
+        fn, (view_from_location, view_from_device_id) = _split_importer2(args)
+        flat, _ = self.get_wholememory_handle().get_global_flatten_tensor(*_with_importer(fn, self.dtype, view_from_location,
+                                                                                          view_from_device_id))
         return self.get_tensor_in_window(flat, 0)[0]
 
-    def get_all_chunked_tensor(self, view_from_location, view_from_device_id):
-        ts, offs = self.get_wholememory_handle().get_all_chunked_flatten_tensor(self.dtype, view_from_location,
-                                                                                view_from_device_id)
+    def get_all_chunked_tensor(self, *args):
+        fn, (view_from_location, view_from_device_id) = _split_importer2(args)
+        ts, offs = self.get_wholememory_handle().get_all_chunked_flatten_tensor(*_with_importer(fn, self.dtype, view_from_location,
+                                                                                                view_from_device_id))
         out_t, out_o = [], []
         for t, o in zip(ts, offs):
             tw, ow = self.get_tensor_in_window(t, o)
@@ -557,6 +611,18 @@ class PyWholeMemoryTensor:
         stride = d.strides[0] if d.dim == 2 else 1
         cols = d.sizes[1] if d.dim == 2 else 1
         self.get_wholememory_handle().to_file(d.storage_offset * es, stride * es, cols * es, filename)
+
+
+def _split_importer2(args):
+    if len(args) == 3 and callable(args[0]):
+        return args[0], args[1:]
+    if len(args) != 2:
+        raise TypeError("expected ([import_dlpack_fn,] view_from_location, view_from_device_id)")
+    return None, args
+
+
+def _with_importer(fn, *rest):
+    return ((fn,) + rest) if fn else rest
 
 
 def malloc(total_size, py_comm, memory_type, memory_location, data_granularity, rank_entry_partition=None):
@@ -629,6 +695,146 @@ def _env_ptr(p_env_fns_int):
     return ctypes.cast(c_void_p(p_env_fns_int), POINTER(_lib.EnvFns))
 
 
+# --------------------------------------------------------------------------- allocation callbacks, reference protocol
+class PyMemoryAllocType:
+    """The allocation kind handed to a malloc callback (reference pyx:348-364)."""
+
+    def __init__(self):
+        self.alloc_type = int(WholeMemoryMemoryAllocType.MatNone)
+
+    def set_type(self, new_type):
+        self.alloc_type = int(new_type)
+
+    def get_type(self):
+        return self.alloc_type
+
+    set_ctype = set_type
+    get_ctype = get_type
+
+
+class GlobalContextWrapper:
+    """wholememory_env_func_t built from Python callables, with the reference binding's calling convention
+    (pyx:366-552), so code written against pylibwholegraph's binding runs unchanged:
+
+        temp_create_context_fn(global_context) -> memory_context (any Python object; kept alive until destroyed)
+        temp_destroy_context_fn(memory_context, global_context)
+        malloc_fn(PyWholeMemoryTensorDescription, PyMemoryAllocType, memory_context, global_context) -> address (int)
+        free_fn(memory_context, global_context)
+
+    OUTPUT memory contexts are Python objects owned by the caller, passed to the ops as id(obj).
+    (wholegraph_b200.torch.wholegraph_env carries a leaner torch-specific table; this one is the general form.)"""
+
+    def __init__(self):
+        self.env = _lib.EnvFns()
+        self._fns = None
+        self._live_temp = {}  # id -> memory context created on behalf of the library
+
+    def create_context(self, temp_create_context_fn, temp_destroy_context_fn, temp_malloc_fn, temp_free_fn, temp_global_context,
+                       output_malloc_fn, output_free_fn, output_global_context):
+        def obj(address):
+            return ctypes.cast(c_void_p(address), ctypes.py_object).value
+
+        def describe(desc_ptr, malloc_type):
+            d = PyWholeMemoryTensorDescription()
+            ctypes.memmove(byref(d.tensor_description), desc_ptr, ctypes.sizeof(_lib.TensorDescription))
+            k = PyMemoryAllocType()
+            k.set_type(malloc_type)
+            return d, k
+
+        def c_create(out_ctx, _g):
+            ctx = temp_create_context_fn(temp_global_context)
+            self._live_temp[id(ctx)] = ctx
+            out_ctx[0] = id(ctx)
+
+        def c_destroy(memory_context, _g):
+            ctx = self._live_temp.pop(memory_context, None)
+            if ctx is not None:
+                temp_destroy_context_fn(ctx, temp_global_context)
+
+        def c_temp_malloc(desc_ptr, malloc_type, memory_context, _g):
+            d, k = describe(desc_ptr, malloc_type)
+            return int(temp_malloc_fn(d, k, self._live_temp[memory_context], temp_global_context) or 0)
+
+        def c_temp_free(memory_context, _g):
+            ctx = self._live_temp.get(memory_context)
+            if ctx is not None:
+                temp_free_fn(ctx, temp_global_context)
+
+        def c_out_malloc(desc_ptr, malloc_type, memory_context, _g):
+            d, k = describe(desc_ptr, malloc_type)
+            return int(output_malloc_fn(d, k, obj(memory_context), output_global_context) or 0)
+
+        def c_out_free(memory_context, _g):
+            output_free_fn(obj(memory_context), output_global_context)
+
+        self._fns = (_lib.CREATE_CTX_FN(c_create), _lib.DESTROY_CTX_FN(c_destroy), _lib.MALLOC_FN(c_temp_malloc), _lib.FREE_FN(c_temp_free),
+                     _lib.MALLOC_FN(c_out_malloc), _lib.FREE_FN(c_out_free))
+        t, o = self.env.temporary_fns, self.env.output_fns
+        t.create_memory_context_fn, t.destroy_memory_context_fn, t.malloc_fn, t.free_fn = self._fns[:4]
+        o.malloc_fn, o.free_fn = self._fns[4:]
+        t.global_context = o.global_context = None
+
+    def get_env_fns(self) -> int:
+        return ctypes.addressof(self.env)
+
+
+def wholememory_env_test_cython_op(input, output, output_variable_device_tensor_handle, output_variable_pinned_tensor_handle,
+                                   output_variable_host_tensor_handle, output_variable_entry_count, p_env_fns_int, stream_int):
+    """Allocator-plumbing self test (reference pyx:1919-1935): output[i, :] = input + i, also into three variable-size
+    outputs allocated through the env functions (device, pinned, host)."""
+    _chk(lib.wholememory_env_test_op(c_void_p(input.get_c_handle()), c_void_p(output.get_c_handle()),
+                                     c_void_p(output_variable_device_tensor_handle), c_void_p(output_variable_pinned_tensor_handle),
+                                     c_void_p(output_variable_host_tensor_handle), output_variable_entry_count, _env_ptr(p_env_fns_int),
+                                     c_void_p(stream_int)))
+
+
+class DLDeviceType(enum.IntEnum):
+    kDLCPU = 1
+    kDLCUDA = 2
+    kDLCUDAHost = 3
+
+
+globals().update(DLDeviceType.__members__)  # module-level constants, like a cpdef enum
+
+
+class PyWholeMemoryFlattenDlpack:
+    """DLPack-exporting flat view of a WholeMemory handle (reference pyx:1105-1290).  The reference builds the DLPack
+    capsule by hand; here the view is a torch tensor over the same memory, which already speaks the protocol."""
+
+    typestr = None
+
+    def __init__(self):
+        self.device_type = WholeMemoryMemoryLocation.MlHost
+        self.device_id = 0
+        self._view = None
+
+    @property
+    def ptr(self):
+        return self._view.data_ptr() if self._view is not None else 0
+
+    def set_view_device(self, device_type, device_id):
+        self.device_type, self.device_id = WholeMemoryMemoryLocation(device_type), int(device_id)
+
+    def get_view(self, handle, data_type, view_type, target_rank):
+        """-> (element count, element offset of the view inside the whole allocation)"""
+        view_type = WholeMemoryViewType(view_type)
+        if view_type == WholeMemoryViewType.VtLocal:
+            self._view, off = handle._local_flat(data_type, self.device_type, self.device_id)
+        elif view_type == WholeMemoryViewType.VtGlobal:
+            self._view, off = handle._global_flat(data_type, self.device_type, self.device_id)
+        else:
+            views, offs = handle._chunked_flat(data_type, self.device_type, self.device_id)
+            self._view, off = views[target_rank], offs[target_rank]
+        self.typestr = get_type_string(data_type)
+        return self._view.numel(), off
+
+    def __dlpack__(self, stream=None):
+        return self._view.__dlpack__() if stream is None else self._view.__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return self._view.__dlpack_device__()
+
+
 def wholememory_gather_op(wholememory_tensor, indices_tensor, output_tensor, p_env_fns_int, stream_int,
                           gather_sms=-1):
     _chk(lib.wholememory_gather(wholememory_tensor.wholememory_tensor, c_void_p(indices_tensor.get_c_handle()),
@@ -691,6 +897,8 @@ def host_generate_random_positive_int(random_seed, sub_sequence, output):
 
 # --------------------------------------------------------------------------- embedding
 class WholeMemoryOptimizer:
+    param_dict = None
+
     def __init__(self):
         self.wm_optimizer = c_void_p(None)
         self.optimizer_type = WholeMemoryOptimizerType.OptNone
