@@ -174,9 +174,9 @@ class WholeMemoryEmbedding(object):
     def apply_gradients(self, lr: float):
         """One wholememory_embedding_gather_gradient_apply over everything recorded since the last call (collective)."""
         indices, grads = torch.cat(self.sparse_indices), torch.cat(self.sparse_grads)
-        self.sparse_indices, self.sparse_grads = [], []
         wmb.EmbeddingGatherGradientApply(self.wmb_embedding, wrap_torch_tensor(indices), wrap_torch_tensor(grads), self.adjust_cache,
                                          lr, get_wholegraph_env_fns(), get_stream())
+        self.sparse_indices, self.sparse_grads = [], []
         self.need_apply = False
 
     def writeback_all_cache(self):
