@@ -15,7 +15,7 @@ from .tensor import WholeMemoryTensor
 from .utils import (get_file_size, str_to_wmb_wholememory_access_type, str_to_wmb_wholememory_location,
                     str_to_wmb_wholememory_memory_type, str_to_wmb_wholememory_optimizer_type,
                     torch_dtype_to_wholememory_dtype)
-from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
+from .wholegraph_env import current_output_device, get_stream, get_wholegraph_env_fns, wrap_torch_tensor
 
 
 class WholeMemoryOptimizer(object):
@@ -159,7 +159,7 @@ class WholeMemoryEmbedding(object):
         assert indice.dim() == 1
         table = self.get_embedding_tensor()
         track = is_training and self.need_grad()
-        rows = torch.empty([indice.shape[0], table.shape[1]], device="cuda:%d" % torch.cuda.current_device(),
+        rows = torch.empty([indice.shape[0], table.shape[1]], device=current_output_device(),
                            dtype=table.dtype if force_dtype is None else force_dtype, requires_grad=track)
         if track:
             self.need_apply = True

@@ -8,7 +8,7 @@ from .. import binding as wmb
 from .comm import WholeMemoryCommunicator
 from .utils import (count_file_entries, get_part_file_list, get_part_file_name, str_to_wmb_wholememory_location,
                     str_to_wmb_wholememory_memory_type, torch_dtype_to_wholememory_dtype, wholememory_dtype_to_torch_dtype)
-from .wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
+from .wholegraph_env import current_output_device, get_stream, get_wholegraph_env_fns, wrap_torch_tensor
 
 WholeMemoryMemoryType = wmb.WholeMemoryMemoryType
 WholeMemoryMemoryLocation = wmb.WholeMemoryMemoryLocation
@@ -56,7 +56,7 @@ class WholeMemoryTensor(object):
     def gather(self, indice: torch.Tensor, *, force_dtype: Union[torch.dtype, None] = None):
         """rows[i, :] = self[indice[i], :] as a new tensor on the current CUDA device (dtype of the table unless forced)."""
         assert indice.dim() == 1
-        rows = torch.empty([indice.shape[0], self.shape[1]], device="cuda:%d" % torch.cuda.current_device(),
+        rows = torch.empty([indice.shape[0], self.shape[1]], device=current_output_device(),
                            dtype=self.dtype if force_dtype is None else force_dtype, requires_grad=False)
         wmb.wholememory_gather_op(self.wmb_tensor, wrap_torch_tensor(indice), wrap_torch_tensor(rows),
                                   get_wholegraph_env_fns(), get_stream())

@@ -71,6 +71,11 @@ def _retire_default_context():
     default_wholegraph_env_context = None
 
 
+def current_output_device() -> str:
+    """Where op outputs are allocated: the current CUDA device (one place, so host-only tests can redirect it)."""
+    return "cuda:%d" % torch.cuda.current_device()
+
+
 def get_stream():
     cuda_stream = torch.cuda.current_stream()._as_parameter_
     return cuda_stream.value if cuda_stream.value is not None else 0
