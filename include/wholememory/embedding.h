@@ -38,71 +38,51 @@ enum wholememory_optimizer_type_t {
   WHOLEMEMORY_OPT_ADAGRAD,
 };
 
-wholememory_error_code_t wholememory_create_embedding_optimizer(
-  wholememory_embedding_optimizer_t* optimizer, wholememory_optimizer_type_t optimizer_type);
+wholememory_error_code_t wholememory_create_embedding_optimizer(wholememory_embedding_optimizer_t* optimizer,
+    wholememory_optimizer_type_t optimizer_type);
 /* parameter_name in {"weight_decay","epsilon","beta1","beta2","adam_w","alpha"}; value -> float */
-wholememory_error_code_t wholememory_optimizer_set_parameter(
-  wholememory_embedding_optimizer_t optimizer, const char* parameter_name, void* value);
+wholememory_error_code_t wholememory_optimizer_set_parameter(wholememory_embedding_optimizer_t optimizer,
+    const char* parameter_name, void* value);
 void wholememory_destroy_embedding_optimizer(wholememory_embedding_optimizer_t optimizer);
 
 /* cache_ratio must lie in [1/512, 1] */
 wholememory_error_code_t wholememory_create_embedding_cache_policy(
-  wholememory_embedding_cache_policy_t* cache_policy,
-  wholememory_comm_t cache_level_comm,
-  wholememory_memory_type_t memory_type,
-  wholememory_memory_location_t memory_location,
-  wholememory_access_type_t access_type,
-  float cache_ratio);
+    wholememory_embedding_cache_policy_t* cache_policy, wholememory_comm_t cache_level_comm,
+    wholememory_memory_type_t memory_type, wholememory_memory_location_t memory_location,
+    wholememory_access_type_t access_type, float cache_ratio);
 wholememory_error_code_t wholememory_destroy_embedding_cache_policy(
-  wholememory_embedding_cache_policy_t cache_policy);
+    wholememory_embedding_cache_policy_t cache_policy);
 
 /* Collective.  The stored row stride is padded to a multiple of 16 bytes; the tensor returned by
  * wholememory_embedding_get_embedding_tensor is the [N, D] view of it. */
-wholememory_error_code_t wholememory_create_embedding(
-  wholememory_embedding_t* wholememory_embedding,
-  wholememory_tensor_description_t* embedding_tensor_description,
-  wholememory_comm_t comm,
-  wholememory_memory_type_t memory_type,
-  wholememory_memory_location_t memory_location,
-  wholememory_embedding_cache_policy_t cache_policy,
-  size_t* embedding_entry_partition = nullptr,
-  int user_defined_sms              = -1,
-  int round_robin_size              = 0);
-wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t wholememory_embedding);
-wholememory_tensor_t wholememory_embedding_get_embedding_tensor(
-  wholememory_embedding_t wholememory_embedding);
+wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* embedding,
+    wholememory_tensor_description_t* embedding_tensor_description, wholememory_comm_t comm,
+    wholememory_memory_type_t memory_type, wholememory_memory_location_t memory_location,
+    wholememory_embedding_cache_policy_t cache_policy, size_t* embedding_entry_partition = nullptr,
+    int user_defined_sms = -1, int round_robin_size = 0);
+wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t embedding);
+wholememory_tensor_t wholememory_embedding_get_embedding_tensor(wholememory_embedding_t embedding);
 /* at most once, before training; fp32 embeddings only; allocates the optimizer state tables */
-wholememory_error_code_t wholememory_embedding_set_optimizer(
-  wholememory_embedding_t wholememory_embedding, wholememory_embedding_optimizer_t optimizer);
+wholememory_error_code_t wholememory_embedding_set_optimizer(wholememory_embedding_t embedding,
+    wholememory_embedding_optimizer_t optimizer);
 
-wholememory_error_code_t wholememory_embedding_gather(wholememory_embedding_t wholememory_embedding,
-                                                      wholememory_tensor_t indices,
-                                                      wholememory_tensor_t output,
-                                                      bool adjust_cache,
-                                                      wholememory_env_func_t* p_env_fns,
-                                                      int64_t stream_int);
+wholememory_error_code_t wholememory_embedding_gather(wholememory_embedding_t embedding,
+    wholememory_tensor_t indices, wholememory_tensor_t output, bool adjust_cache, wholememory_env_func_t* env_fns,
+    int64_t stream_int);
 /* Collective.  indices/grads are this rank's (row id, fp32 gradient row) pairs; gradients of
  * duplicate ids (from any rank) are summed, then the owner applies ONE optimizer step per row. */
-wholememory_error_code_t wholememory_embedding_gather_gradient_apply(
-  wholememory_embedding_t wholememory_embedding,
-  wholememory_tensor_t indices,
-  wholememory_tensor_t grads,
-  bool adjust_cache,
-  float lr,
-  wholememory_env_func_t* p_env_fns,
-  int64_t stream_int);
+wholememory_error_code_t wholememory_embedding_gather_gradient_apply(wholememory_embedding_t embedding,
+    wholememory_tensor_t indices, wholememory_tensor_t grads, bool adjust_cache, float lr,
+    wholememory_env_func_t* env_fns, int64_t stream_int);
 
 /* nullptr-terminated list, e.g. {"m","v","beta12t",nullptr} for LazyAdam */
 const char* const* wholememory_embedding_get_optimizer_state_names(
-  wholememory_embedding_t wholememory_embedding);
-wholememory_tensor_t wholememory_embedding_get_optimizer_state(
-  wholememory_embedding_t wholememory_embedding, const char* name);
+  wholememory_embedding_t embedding);
+wholememory_tensor_t wholememory_embedding_get_optimizer_state(wholememory_embedding_t embedding, const char* name);
 
 /* no cache in this build: both succeed as no-ops */
-wholememory_error_code_t wholememory_embedding_writeback_cache(
-  wholememory_embedding_t wholememory_embedding, int64_t stream_int);
-wholememory_error_code_t wholememory_embedding_drop_all_cache(
-  wholememory_embedding_t wholememory_embedding, int64_t stream_int);
+wholememory_error_code_t wholememory_embedding_writeback_cache(wholememory_embedding_t embedding, int64_t stream_int);
+wholememory_error_code_t wholememory_embedding_drop_all_cache(wholememory_embedding_t embedding, int64_t stream_int);
 
 #ifdef __cplusplus
 }

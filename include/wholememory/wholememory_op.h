@@ -21,31 +21,19 @@ extern "C" {
  * Asynchronous on `stream` for CONTINUOUS/CHUNKED (and peer-mapped DISTRIBUTED) tables.
  * gather_sms: SM budget for the kernel, -1 = all.
  */
-wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_tensor,
-                                            wholememory_tensor_t indices_tensor,
-                                            wholememory_tensor_t output_tensor,
-                                            wholememory_env_func_t* p_env_fns,
-                                            void* stream,
-                                            int gather_sms = -1);
+wholememory_error_code_t wholememory_gather(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor,
+    wholememory_tensor_t output_tensor, wholememory_env_func_t* env_fns, void* stream, int gather_sms = -1);
 
 /* table[indices[i], :] = convert(input[i, :]); negative indices skipped; duplicate indices race
  * (last writer wins, as in the reference). */
-wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor,
-                                             wholememory_tensor_t indices_tensor,
-                                             wholememory_tensor_t wholememory_tensor,
-                                             wholememory_env_func_t* p_env_fns,
-                                             void* stream,
-                                             int scatter_sms = -1);
+wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor, wholememory_tensor_t indices_tensor,
+    wholememory_tensor_t wm_tensor, wholememory_env_func_t* env_fns, void* stream, int scatter_sms = -1);
 
 /* allocator-plumbing self test used by the binding's unit test (reference wholememory_op.h:70-78) */
 wholememory_error_code_t wholememory_env_test_op(wholememory_tensor_t input_tensor,
-                                                 wholememory_tensor_t output_fixed_tensor,
-                                                 void* output_variable_device_tensor_handle,
-                                                 void* output_variable_pinned_tensor_handle,
-                                                 void* output_variable_host_tensor_handle,
-                                                 int64_t output_variable_entry_count,
-                                                 wholememory_env_func_t* p_env_fns,
-                                                 void* stream);
+    wholememory_tensor_t output_fixed_tensor, void* output_variable_device_tensor_handle,
+    void* output_variable_pinned_tensor_handle, void* output_variable_host_tensor_handle,
+    int64_t output_variable_entry_count, wholememory_env_func_t* env_fns, void* stream);
 
 #ifdef __cplusplus
 }
