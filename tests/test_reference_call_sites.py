@@ -136,3 +136,55 @@ def test_attribute_reads_on_aliased_modules_exist():
                     and node.attr not in OUT_OF_SCOPE_NAMES and not hasattr(aliases[node.value.id], node.attr):
                 missing.add("%s:%d %s.%s" % (os.path.relpath(f, REF_PY), node.lineno, node.value.id, node.attr))
     assert not missing, sorted(missing)
+
+
+def _our_methods():
+    import wholegraph_b200.binding as wmb
+    import wholegraph_b200.torch as wgth
+    import wholegraph_b200.torch.wholegraph_env as env
+    methods = {}
+    for mod in (wmb, wgth, env):
+        for cname, cls in inspect.getmembers(mod, inspect.isclass):
+            if cls.__module__.startswith("wholegraph_b200"):
+                for mname, fn in inspect.getmembers(cls, inspect.isfunction):
+                    if not mname.startswith("__"):
+                        methods.setdefault(mname, {})[cname] = fn
+    return methods
+
+
+# method names that belong to something else at that call site (torch.Tensor.scatter / torch.gather on plain tensors in the
+# reference's op test, torch.utils.cpp_extension.load)
+NOT_OUR_OBJECT = {("tests/wholegraph_torch/ops/test_wholegraph_gather_scatter.py", "scatter"),
+                  ("tests/wholegraph_torch/ops/test_wholegraph_gather_scatter.py", "gather"), ("torch/wholegraph_env.py", "load")}
+
+
+def test_method_calls_bind_to_a_class_of_this_implementation():
+    """`obj.method(...)` calls whose method name one of this repo's binding / torch classes defines: the call shape must bind
+    to at least one of them (the receiver's type is not known statically)."""
+    methods = _our_methods()
+    checked, problems = 0, []
+    for f in _files():
+        tree = ast.parse(open(f).read(), f)
+        aliases = _aliases(tree, f)
+        rel = os.path.relpath(f, REF_PY)
+        for node in ast.walk(tree):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in methods):
+                continue
+            if isinstance(node.func.value, ast.Name) and node.func.value.id in aliases:
+                continue  # module-level call, covered above
+            if (rel, node.func.attr) in NOT_OUR_OBJECT:
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args) or any(k.arg is None for k in node.keywords):
+                continue
+            checked += 1
+            for fn in methods[node.func.attr].values():
+                try:
+                    inspect.signature(fn).bind(None, *[None] * len(node.args), **{k.arg: None for k in node.keywords})
+                    break
+                except TypeError:
+                    pass
+            else:
+                problems.append("%s:%d .%s(%d positional, keywords %s)" % (rel, node.lineno, node.func.attr, len(node.args),
+                                                                          [k.arg for k in node.keywords]))
+    assert not problems, "\n".join(problems)
+    assert checked > 200, checked
