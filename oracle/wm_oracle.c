@@ -11,14 +11,18 @@
  *       (cpp/tests/wholememory_ops/embedding_test_utils.cu:197-238) in tests/test_oracle.py, against an
  *       independent numpy restatement, and against the reference's own GPU kernels rebuilt from
  *       /root/reference (oracle/_ref/libwholegraph_ref.so) on the GPU box (tests/test_ref_parity.py).
- *   sparse optimizers            : restated from the kernels AND from the reference's CPU test model
- *       (cpp/tests/wholememory_ops/wholememory_embedding_gradient_apply_tests.cu:169-371); tolerance
- *       1e-5 is the reference's own (:481-501).  The optimizer TU does not compile here without RAFT,
- *       so there is no reference-binary pin: "parity unpinned beyond the reference's CPU model".
- *   neighbor sampler             : the selection algorithm is pinned against the reference's CPU
- *       restatement (cpp/tests/wholegraph_ops/graph_sampling_test_utils.cu:306-321); the RANDOM STREAM
- *       (RAFT PCGenerator, un-vendored dependency rapidsai/raft branch-24.12) is restated from the
- *       published PCG-XSH-RR 64/32 algorithm and is "parity unpinned" (no RAFT source/golden here).
+ *   sparse optimizers            : restated from the kernels; pinned on CPU against the reference's own CPU test model
+ *       compiled as code (class CPUOptimizer, cpp/tests/wholememory_ops/wholememory_embedding_gradient_apply_tests.cu:169-371,
+ *       built by oracle/build_ref_host_optimizer_model.sh): bit-identical over multi-step schedules with duplicate ids
+ *       (tests/test_ref_optimizer_model.py); the asserted tolerance stays the reference's own 1e-5 (:481-501).  The
+ *       reference's optimizer kernels also build into oracle/_ref (RAFT stubbed by a declaration); the GPU comparison
+ *       with them (tests/test_zz_ref_optimizer_parity_gpu.py) has not run on a B200 yet.
+ *   neighbor sampler             : the selection algorithms are pinned against the reference's CPU models compiled as
+ *       code (cpp/tests/wholegraph_ops/graph_sampling_test_utils.cu:419-505 and :676-763, built by
+ *       oracle/build_ref_host_sampling_model.sh; tests/test_ref_sampling_model.py, element for element).  The RANDOM
+ *       STREAM (RAFT PCGenerator, un-vendored dependency rapidsai/raft branch-24.12) is restated from the published
+ *       PCG-XSH-RR 64/32 algorithm and checked against the pcg32 known-answer vector, not against RAFT itself:
+ *       "parity unpinned" for the stream (no RAFT source / golden here).
  */
 #include <math.h>
 #include <pthread.h>
