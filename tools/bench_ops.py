@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Device-timed micro-benchmarks of the other hot-path kernels (scatter, fused LazyAdam step, neighbor sampling) with
-their roofline arithmetic.  One GPU, world_size 1.  Not the headline metric (that is bench.py)."""
+"""Device-timed micro-benchmarks of the other hot-path kernels (--what scatter,adam,refadam,sample and, for the rows
+DESIGN.md section 9 lists as not yet timed, unique,selfloop,weighted,budget) with their roofline arithmetic.  One GPU, world_size 1.  Not the headline metric (that is bench.py)."""
 import argparse
 import json
 import os
@@ -129,6 +129,72 @@ def main():
                         "ms": round(ms, 4), "Msamples_per_s": round(total / ms / 1e3, 2), "samples": total})
         wgth.destroy_wholememory_tensor(rp)
         wgth.destroy_wholememory_tensor(cp)
+    if "unique" in args.what:
+        # f1: the op between two sampling hops -- targets = one hop's centers, neighbors = its samples (C5 shape: 25 per center)
+        for targets, per in ((1024, 25), (25 * 1024, 10), (262144, 25)):
+            tg = torch.randperm(50_000_000, device="cuda", generator=g)[:targets].contiguous()
+            nb = torch.randint(0, 50_000_000, (targets * per,), device="cuda", generator=g)
+
+            def f():
+                return wgth.graph_ops.append_unique(tg, nb, need_neighbor_raw_to_unique=True)
+            ms = timeit(f, steps=10, warmup=3)
+            uniq = int(f()[0].shape[0])
+            alg = (targets + targets * per) * 8 + uniq * 8 + targets * per * 4
+            out.append({"op": "append_unique %d targets + %d neighbors int64 -> %d unique (+ mapping), whole call" % (targets, targets * per, uniq),
+                        "ms": round(ms, 4), "Mids_per_s": round((targets + targets * per) / ms / 1e3, 2), "alg_GBps": round(alg / ms / 1e6, 1)})
+    if "selfloop" in args.what:
+        rows = 262144
+        deg = torch.randint(0, 26, (rows,), device="cuda", generator=g)
+        rp32 = torch.zeros(rows + 1, dtype=torch.int32, device="cuda")
+        rp32[1:] = torch.cumsum(deg, 0).to(torch.int32)
+        col32 = torch.randint(0, rows * 4, (int(rp32[-1].item()),), device="cuda", dtype=torch.int32, generator=g)
+
+        def f():
+            return wgth.graph_ops.add_csr_self_loop(rp32, col32)
+        ms = timeit(f, steps=10, warmup=3)
+        alg = 2 * (rows + 1) * 4 + col32.numel() * 4 * 2 + rows * 4
+        out.append({"op": "csr_add_self_loop %d rows, %d edges" % (rows, col32.numel()), "ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1)})
+    if "weighted" in args.what:
+        nodes = 10_000_000
+        deg = torch.clamp((torch.rand(nodes, device="cuda", generator=g) ** -0.7).long(), max=10000)
+        row_ptr = torch.zeros(nodes + 1, dtype=torch.int64, device="cuda")
+        row_ptr[1:] = torch.cumsum(deg, 0)
+        edges = int(row_ptr[-1].item())
+        rp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [nodes + 1], torch.int64, [1])
+        cp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [edges], torch.int32, [1])
+        wp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [edges], torch.float32, [1])
+        rp.get_local_tensor()[0].copy_(row_ptr)
+        cp.get_local_tensor()[0].copy_(torch.randint(0, nodes, (edges,), device="cuda", dtype=torch.int32, generator=g))
+        wp.get_local_tensor()[0].copy_(torch.rand(edges, device="cuda", generator=g) + 0.01)
+        for ncenter, k in ((1024, 25), (262144, 25), (262144, 10)):
+            centers = torch.randint(0, nodes, (ncenter,), device="cuda", generator=g)
+
+            def f():
+                return wgth.weighted_sample_without_replacement(rp.wmb_tensor, cp.wmb_tensor, wp.wmb_tensor, centers, k, random_seed=7)
+            ms = timeit(f, steps=10, warmup=3)
+            total = int(f()[0][-1].item())
+            out.append({"op": "weighted sample %d centers k=%d on %d-node/%d-edge CSR (whole call)" % (ncenter, k, nodes, edges),
+                        "ms": round(ms, 4), "Msamples_per_s": round(total / ms / 1e3, 2), "samples": total})
+        for t in (rp, cp, wp):
+            wgth.destroy_wholememory_tensor(t)
+    if "budget" in args.what:
+        # f2: gather under an SM budget (the persistent-grid mode a loader uses to overlap sampling with the gather)
+        rows, dim, n = args.rows, 256, 1 << 20
+        t = wgth.create_wholememory_tensor(comm, "continuous", "cuda", [rows, dim], torch.float32, [dim, 1])
+        idxs = [torch.randint(0, rows, (n,), device="cuda", generator=g) for _ in range(4)]
+        dst = torch.empty(n, dim, device="cuda")
+        w_dst, w_idx = wrap_torch_tensor(dst), [wrap_torch_tensor(i) for i in idxs]
+        for sms in (-1, 132, 96, 64, 32):
+            k = [0]
+
+            def f():
+                wmb.wholememory_gather_op(t.wmb_tensor, w_idx[k[0] % 4], w_dst, env, get_stream(), sms)
+                k[0] += 1
+            ms = timeit(f)
+            alg = n * (dim * 4 * 2 + 8)
+            out.append({"op": "gather fp32 %dx%d, %d rows, gather_sms=%d" % (rows, dim, n, sms), "ms": round(ms, 4),
+                        "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
+        wgth.destroy_wholememory_tensor(t)
     for o in out:
         print(json.dumps(o))
 

@@ -43,6 +43,8 @@ cat gpurun_out/${R}_gather_c2_full_summary.txt
 
 step "4. other kernels, the reference's optimizer kernels next to ours, native env A/B on the sampler"
 timeout 600 python tools/bench_ops.py 2>&1 | tail -8
+# the rows DESIGN.md section 9 still lists as "not timed": append_unique, self loop, weighted sampler, gather under an SM budget
+timeout 900 python tools/bench_ops.py --what unique,selfloop,weighted,budget 2>&1 | tail -16
 WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 600 python tools/bench_ops.py --what refadam 2>&1 | tail -3
 # the reference's WHOLE wholememory_embedding_gather_gradient_apply (its embedding layer is built into oracle/_ref): same tool, other library
 WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 600 python tools/bench_ops.py --what adam 2>&1 | tail -3
