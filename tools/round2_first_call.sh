@@ -64,3 +64,6 @@ timeout 600 $B -t 1 -l 1 -e 102400000000 -g 1073741824 -d 256 -c 20 -n 1 --lib o
 step "5. sanitizers on the smoke pass (every kernel of the hot path once; SURVEY section 5)"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_$R.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|smoke OK" gpurun_out/sanitizer_memcheck_$R.log | tail -3
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_$R.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|smoke OK" gpurun_out/sanitizer_racecheck_$R.log | tail -3
+
+step "6. golden vectors from the reference binary for the optimizer / sampler / graph-op kernels (copy into tests/golden/ afterwards)"
+bash tools/make_golden.sh 2>&1 | tail -6
