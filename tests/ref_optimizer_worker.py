@@ -21,7 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-ROWS = 3000
+SMALL = os.environ.get("WG_GOLDEN_SMALL") == "1"  # compact sizes for the committed golden vectors (tools/make_golden.sh)
+ROWS = 100 if SMALL else 3000
 STEPS = 3
 LR = 0.05
 # (kind, params, dim, index dtype, gradients per step)
@@ -42,6 +43,7 @@ OPT_ID = {"sgd": 1, "adam": 2, "rmsprop": 3, "adagrad": 4}  # wholememory_optimi
 def case_inputs(ci):
     """Initial weights and the per-step (indices, gradients): valid ids only, heavy duplication (Zipf)."""
     kind, params, dim, idt, n = CASES[ci]
+    n = max(40, n // 25) if SMALL else n
     rng = np.random.default_rng(4242 + ci)
     w0 = rng.standard_normal((ROWS, dim)).astype(np.float32)
     steps = []

@@ -15,6 +15,20 @@ sys.path.insert(0, HERE)
 GOLD = os.path.join(HERE, "golden")
 
 
+WORKERS = ("ref_sample_worker", "ref_optimizer_worker", "ref_graph_ops_worker", "test_zz_ref_optimizer_parity_gpu")
+
+
+@pytest.fixture(autouse=True)
+def _compact_case_lists(monkeypatch):
+    """The fixtures were made with WG_GOLDEN_SMALL=1 (compact sizes); the workers read it at import."""
+    monkeypatch.setenv("WG_GOLDEN_SMALL", "1")
+    for m in WORKERS:
+        sys.modules.pop(m, None)
+    yield
+    for m in WORKERS:
+        sys.modules.pop(m, None)
+
+
 def _gold(name):
     path = os.path.join(GOLD, "reference_%s_golden.npz" % name)
     if not os.path.exists(path):

@@ -14,6 +14,6 @@ ls -la gpurun_out/reference_gather_scatter_golden.npz
 #   cp gpurun_out/reference_{optimizer,sampler,graph_ops}_golden.npz tests/golden/
 for w in optimizer:ref_optimizer_worker sampler:ref_sample_worker graph_ops:ref_graph_ops_worker; do
   name=${w%%:*}; worker=${w##*:}
-  WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 900 python tests/$worker.py gpurun_out/reference_${name}_golden.npz \
+  WG_GOLDEN_SMALL=1 WHOLEGRAPH_B200_LIB=oracle/_ref/libwholegraph_ref.so timeout 900 python tests/$worker.py gpurun_out/reference_${name}_golden.npz \
     && ls -la gpurun_out/reference_${name}_golden.npz || echo "golden for $name: worker failed"
 done
