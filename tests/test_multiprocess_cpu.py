@@ -39,6 +39,13 @@ def _worker(rank, world_size, port, results):
         sub = wgth.split_communicator(comm, color=rank % 2, key=0)
         assert sub.get_size() == (world_size + 1 - rank % 2) // 2 and sub.get_rank() == rank // 2
         sub.destroy()
+        # key decides the order inside the new communicator (ties by old rank): descending keys reverse the ranks
+        rev = wgth.split_communicator(comm, color=0, key=world_size - rank)
+        assert rev.get_size() == world_size and rev.get_rank() == world_size - 1 - rank
+        rev.barrier()
+        rev.destroy()
+        # a negative color opts out (the Python helper answers None without entering the collective, like the reference's)
+        assert wgth.split_communicator(comm, color=-1) is None
         # a second communicator in the reverse order of creation still matches ranks up
         comm2 = wgth.create_group_communicator()
         assert comm2.get_rank() == rank
