@@ -271,6 +271,58 @@ def scenario_file_io(rank, world, comm):
             os.remove(f)
 
 
+def scenario_file_io_grid(rank, world, comm):
+    """The reference's load / store test grid (python/pylibwholegraph/.../tests/pylibwholegraph/test_wholememory_io.py:177-186,
+    :344-351; round_robin_size 0 only): part-file counts {3, 5}, embedding dim {16, 31, 33} inside row strides {32, 64},
+    storage offsets {0, 3} (a column window of a wider table), default / random row partitions, every memory type.  After a
+    load the window holds the file rows and the columns outside it keep their sentinel; a store writes exactly the window."""
+    import tempfile
+    import torch
+    import wholegraph_b200.torch as wgth
+    rows = 1537
+    base = os.path.join(tempfile.gettempdir(), "wgb200_iogrid_%s" % os.environ["MASTER_PORT"])
+    cases = [(3, 16, 32, 0, "default", "chunked", "cuda"), (5, 31, 32, 0, "random", "continuous", "cuda"),
+             (3, 33, 64, 3, "random", "distributed", "cuda"), (5, 16, 64, 3, "default", "chunked", "cpu"),
+             (3, 31, 64, 3, "random", "continuous", "cpu"), (5, 33, 64, 0, "default", "chunked", "cuda")]
+    for ci, (parts, dim, stride, off, method, mt, loc) in enumerate(cases):
+        rng = np.random.default_rng(4000 + ci)  # same stream on every rank
+        host = rng.standard_normal((rows, dim)).astype(np.float32)
+        cuts = [0] + sorted(rng.choice(np.arange(1, rows), size=parts - 1, replace=False).tolist()) + [rows]
+        partition = _random_partition(rng, rows, world) if (method == "random" and world > 1) else None
+        files = ["%s_c%d_part_%d_of_%d" % (base, ci, i, parts) for i in range(parts)]
+        if rank == 0:
+            for i, f in enumerate(files):
+                host[cuts[i]:cuts[i + 1]].copy().tofile(f)
+        comm.barrier()
+        root = wgth.create_wholememory_tensor(comm, mt, loc, [rows, stride], torch.float32, [stride, 1], partition)
+        whole_local, first = root.get_local_tensor(host_view=(loc == "cpu"))
+        whole_local.fill_(-7.0)
+        comm.barrier()
+        window = root.get_sub_tensor([0, off], [rows, off + dim])
+        assert tuple(window.shape) == (rows, dim) and window.stride()[0] == stride and window.storage_offset() == off
+        window.from_filelist(files)
+        comm.barrier()
+        mine = whole_local.cpu().numpy()
+        nloc = mine.shape[0]
+        if partition is not None:
+            assert nloc == partition[rank] and first == sum(partition[:rank])
+        assert np.array_equal(mine[:, off:off + dim], host[first:first + nloc]), ("load", ci)
+        outside = np.delete(mine, np.s_[off:off + dim], axis=1)
+        assert np.all(outside == -7.0), ("load wrote outside the column window", ci)
+        # store: every rank writes the window of its rows; the concatenation of the parts is the file content again
+        window.to_file_prefix("%s_c%d_out" % (base, ci))
+        comm.barrier()
+        if rank == 0:
+            back = np.concatenate([np.fromfile("%s_c%d_out_part_%d_of_%d" % (base, ci, r, world), dtype=np.float32) for r in range(world)])
+            assert back.size == rows * dim and np.array_equal(back.reshape(rows, dim), host), ("store", ci)
+        comm.barrier()
+        wgth.destroy_wholememory_tensor(root)
+    if rank == 0:
+        import glob
+        for f in glob.glob(base + "_*"):
+            os.remove(f)
+
+
 def scenario_weighted_sampling(rank, world, comm):
     """Weighted (A-Res) sampler vs the oracle: same sample sets for the same seed.  Keys are float log1pf/exp2f values, so a
     center whose k-th and (k+1)-th keys are within a few ulp may legitimately resolve differently between libm and CUDA:
@@ -322,7 +374,7 @@ def scenario_weighted_sampling(rank, world, comm):
                 wmb.destroy_wholememory_tensor(t)
 
 
-SCENARIOS = {"weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+SCENARIOS = {"file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):
