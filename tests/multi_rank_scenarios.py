@@ -323,6 +323,104 @@ def scenario_file_io_grid(rank, world, comm):
             os.remove(f)
 
 
+def scenario_sampling_grid(rank, world, comm):
+    """The reference's Python sampling test grids (tests/wholegraph_torch/ops/test_wholegraph_unweighted_sample_without_replacement.py
+    :360-369, ..._weighted_...:362-372): graph of 103 / 113 nodes and 1043 edges, 13 centers, fan-out 11 and -1, int32 / int64
+    centers and column ids, CSR in DEVICE and in HOST memory, CONTINUOUS / CHUNKED / DISTRIBUTED, every combination of the two
+    optional outputs -- the number and order of returned tensors follow the flags."""
+    import torch
+    import wholegraph_b200.binding as wmb
+    import wholegraph_b200.torch as wgth
+    from oracle import oracle as O
+    dev = torch.cuda.current_device()
+
+    def make_graph(rng, nodes, edges):
+        deg = rng.multinomial(edges, np.ones(nodes) / nodes)
+        row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        return row_ptr
+
+    def fill(t, host, dt, ml):
+        loc_t, first = t.get_wholememory_handle().get_local_flatten_tensor(dt, ml, dev if ml == wmb.MlDevice else -1)
+        loc_t.copy_(torch.from_numpy(host[first:first + loc_t.numel()]))
+
+    # ---- unweighted
+    rng = np.random.default_rng(360)
+    nodes, edges = 103, 1043
+    row_ptr = make_graph(rng, nodes, edges)
+    for col_np, col_wm in ((np.int32, wmb.DtInt), (np.int64, wmb.DtInt64)):
+        col = rng.integers(0, nodes, size=edges).astype(col_np)
+        for ml in (wmb.MlDevice, wmb.MlHost):
+            for mt in (wmb.MtContinuous, wmb.MtChunked, wmb.MtDistributed):
+                if ml == wmb.MlHost and mt == wmb.MtDistributed and world > 1:
+                    continue  # host DISTRIBUTED shards are private to their rank (no mapping): exchange path, covered by the device case
+                rp = wmb.create_wholememory_array(wmb.DtInt64, nodes + 1, comm.wmb_comm, mt, ml)
+                cp = wmb.create_wholememory_array(col_wm, edges, comm.wmb_comm, mt, ml)
+                fill(rp, row_ptr, wmb.DtInt64, ml)
+                fill(cp, col, col_wm, ml)
+                comm.barrier()
+                for k in (11, -1):
+                    for cen_np in (np.int32, np.int64):
+                        centers = np.random.default_rng(13 + rank).integers(0, nodes, size=13).astype(cen_np)
+                        eo, ed, el, eg = O.unweighted_sample(row_ptr, col.astype(np.int64), centers.astype(np.int64), k, 1000 + k)
+                        for need_lid in (True, False):
+                            for need_gid in (True, False):
+                                res = wgth.unweighted_sample_without_replacement(rp, cp, torch.from_numpy(centers).cuda(), k, random_seed=1000 + k,
+                                                                                 need_center_local_output=need_lid, need_edge_output=need_gid)
+                                assert len(res) == 2 + int(need_lid) + int(need_gid), (len(res), need_lid, need_gid)
+                                assert res[0].dtype == torch.int32 and res[0].cpu().numpy().tolist() == eo.tolist()
+                                assert res[1].cpu().numpy().astype(np.int64).tolist() == ed.tolist(), (k, ml, mt)
+                                pos = 2
+                                if need_lid:
+                                    assert res[pos].cpu().numpy().tolist() == el.tolist()
+                                    pos += 1
+                                if need_gid:
+                                    assert res[pos].dtype == torch.int64 and res[pos].cpu().numpy().tolist() == eg.tolist()
+                comm.barrier()
+                wmb.destroy_wholememory_tensor(rp)
+                wmb.destroy_wholememory_tensor(cp)
+
+    # ---- weighted
+    rng = np.random.default_rng(362)
+    nodes, edges = 113, 1043
+    row_ptr = make_graph(rng, nodes, edges)
+    for col_np, col_wm in ((np.int32, wmb.DtInt), (np.int64, wmb.DtInt64)):
+        col = rng.integers(0, nodes, size=edges).astype(col_np)
+        for w_np, w_wm in ((np.float32, wmb.DtFloat), (np.float64, wmb.DtDouble)):
+            weights = rng.uniform(0.1, 3.0, size=edges).astype(w_np)
+            for ml in (wmb.MlDevice, wmb.MlHost):
+                for mt in (wmb.MtContinuous, wmb.MtChunked):
+                    rp = wmb.create_wholememory_array(wmb.DtInt64, nodes + 1, comm.wmb_comm, mt, ml)
+                    cp = wmb.create_wholememory_array(col_wm, edges, comm.wmb_comm, mt, ml)
+                    wp = wmb.create_wholememory_array(w_wm, edges, comm.wmb_comm, mt, ml)
+                    fill(rp, row_ptr, wmb.DtInt64, ml)
+                    fill(cp, col, col_wm, ml)
+                    fill(wp, weights, w_wm, ml)
+                    comm.barrier()
+                    for cen_np in (np.int32, np.int64):
+                        centers = np.random.default_rng(17 + rank).integers(0, nodes, size=13).astype(cen_np)
+                        eo, ed, el, eg, margin = O.weighted_sample(row_ptr, col.astype(np.int64), weights, centers.astype(np.int64), 11, 77)
+                        for need_lid in (True, False):
+                            for need_gid in (True, False):
+                                res = wgth.weighted_sample_without_replacement(rp, cp, wp, torch.from_numpy(centers).cuda(), 11, random_seed=77,
+                                                                               need_center_local_output=need_lid, need_edge_output=need_gid)
+                                assert len(res) == 2 + int(need_lid) + int(need_gid)
+                                off = res[0].cpu().numpy()
+                                assert off.tolist() == eo.tolist()
+                                dst = res[1].cpu().numpy().astype(np.int64)
+                                for c in range(centers.size):  # per-center sets, the reference's own comparison (segment_sort_output)
+                                    a, b = off[c], off[c + 1]
+                                    if sorted(dst[a:b].tolist()) != sorted(ed[a:b].tolist()):
+                                        assert margin[c] < 1e-5, (c, margin[c])
+                                if need_lid:
+                                    assert res[2].cpu().numpy().tolist() == el.tolist()
+                                if need_gid:
+                                    gid = res[2 + int(need_lid)].cpu().numpy()
+                                    assert np.array_equal(col[gid].astype(np.int64), dst)  # edge ids name the sampled neighbours
+                    comm.barrier()
+                    for t in (rp, cp, wp):
+                        wmb.destroy_wholememory_tensor(t)
+
+
 def scenario_weighted_sampling(rank, world, comm):
     """Weighted (A-Res) sampler vs the oracle: same sample sets for the same seed.  Keys are float log1pf/exp2f values, so a
     center whose k-th and (k+1)-th keys are within a few ulp may legitimately resolve differently between libm and CUDA:
@@ -374,7 +472,7 @@ def scenario_weighted_sampling(rank, world, comm):
                 wmb.destroy_wholememory_tensor(t)
 
 
-SCENARIOS = {"file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+SCENARIOS = {"sampling_grid": scenario_sampling_grid, "file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):
