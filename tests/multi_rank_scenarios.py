@@ -421,6 +421,47 @@ def scenario_sampling_grid(rank, world, comm):
                         wmb.destroy_wholememory_tensor(t)
 
 
+def scenario_gather_scatter_functors(rank, world, comm):
+    """The reference's torch-level op test (tests/wholegraph_torch/ops/test_wholegraph_gather_scatter.py:40-160) with its own
+    sizes: a [1024*256*world + 3, 256] fp32 table under a random row partition, every rank scatters the rows
+    rank, rank + world, ... through wholememory_scatter_functor, the local view is compared with the closed form
+    value(row, col) = row + col, then 100,001 random int32 indices are gathered with wholememory_gather_forward_functor.
+    Every memory type x location the communicator supports."""
+    import torch
+    import wholegraph_b200.binding as wmb
+    from wholegraph_b200.torch import wholememory_ops as wm_ops
+    from wholegraph_b200.torch.dlpack_utils import torch_import_from_dlpack
+    count, dim, n = 1024 * 256 * world + 3, 256, 100001
+    partition = _random_partition(np.random.default_rng(1), count, world) if world > 1 else None
+    dev = torch.cuda.current_device()
+
+    def closed_form(ids):
+        return (ids.to(torch.int64).reshape(-1, 1) + torch.arange(dim, dtype=torch.int64).reshape(1, dim)).to(torch.float32)
+
+    for mt in (wmb.MtContinuous, wmb.MtChunked, wmb.MtDistributed):
+        for ml in (wmb.MlHost, wmb.MlDevice):
+            if not comm.wmb_comm.support_type_location(mt, ml):
+                continue
+            table = wmb.create_wholememory_matrix(wmb.DtFloat, count, dim, -1, comm.wmb_comm, mt, ml, partition)
+            mine = torch.arange(rank, count, world, dtype=torch.int64)
+            wm_ops.wholememory_scatter_functor(closed_form(mine).cuda(), mine.cuda(), table)
+            torch.cuda.synchronize()
+            comm.barrier()
+            local, start = table.get_local_tensor(torch_import_from_dlpack, wmb.MlDevice, dev)  # the reference's call form
+            assert start == table.get_local_entry_start() and tuple(local.shape) == (table.get_local_entry_count(), dim)
+            if partition is not None:
+                assert table.get_local_entry_count() == partition[rank]
+            assert torch.equal(local.cpu(), closed_form(torch.arange(start, start + local.shape[0])))
+            idx = torch.randint(0, count, (n,), dtype=torch.int32, generator=torch.Generator().manual_seed(5 + rank))
+            rows = wm_ops.wholememory_gather_forward_functor(table, idx.cuda())
+            assert rows.dtype == torch.float32 and torch.equal(rows.cpu(), closed_form(idx))
+            half = wm_ops.wholememory_gather_forward_functor(table, idx.cuda()[:1000], torch_output_dtype=torch.float16)
+            assert half.dtype == torch.float16 and torch.equal(half.cpu(), closed_form(idx[:1000]).to(torch.float16))
+            comm.barrier()
+            del local
+            wmb.destroy_wholememory_tensor(table)
+
+
 def scenario_weighted_sampling(rank, world, comm):
     """Weighted (A-Res) sampler vs the oracle: same sample sets for the same seed.  Keys are float log1pf/exp2f values, so a
     center whose k-th and (k+1)-th keys are within a few ulp may legitimately resolve differently between libm and CUDA:
@@ -472,7 +513,7 @@ def scenario_weighted_sampling(rank, world, comm):
                 wmb.destroy_wholememory_tensor(t)
 
 
-SCENARIOS = {"sampling_grid": scenario_sampling_grid, "file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+SCENARIOS = {"gather_scatter_functors": scenario_gather_scatter_functors, "sampling_grid": scenario_sampling_grid, "file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):
