@@ -17,7 +17,8 @@ REF_PY = "/root/reference/python/pylibwholegraph/pylibwholegraph"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF_PY), reason="reference tree not present")
 
 
-OURS = {"pylibwholegraph.binding.wholememory_binding": "wholegraph_b200.binding", "pylibwholegraph.torch": "wholegraph_b200.torch"}
+OURS = {"pylibwholegraph.binding.wholememory_binding": "wholegraph_b200.binding", "pylibwholegraph.torch": "wholegraph_b200.torch",
+        "pylibwholegraph.utils": "wholegraph_b200.utils", "pylibwholegraph.test_utils": "wholegraph_b200.test_utils"}
 # the reference's GNN example glue and launch helpers: outside SURVEY.md section 8
 OUT_OF_SCOPE_FILES = {"gnn_model.py", "data_loader.py", "common_options.py", "distributed_launch.py", "gat_conv.py", "sage_conv.py"}
 # call sites that are wrong in the reference itself: embedding.py:336,339 call get_stream(False), but its get_stream()
