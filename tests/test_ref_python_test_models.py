@@ -80,3 +80,34 @@ def test_reference_python_weighted_model_equals_the_oracle(k, weight_dtype):
             loose += 1
     assert loose <= 1
     assert np.array_equal(col.numpy()[w_gid].astype(np.int64), want[1].numpy().astype(np.int64))
+
+
+def test_reference_python_graph_op_models_equal_the_expectations_of_this_repos_gpu_tests():
+    """The host models of the reference's append_unique / add_csr_self_loop Python tests against the expectations this repo's
+    GPU tests hold the kernels to (tests/test_graph_ops_gpu.py: first-occurrence order, closed-form self-loop CSR)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_graph_ops_gpu as ours
+    loop = _load("test_graph_add_csr_self_loop")
+    uniq = _load("test_graph_append_unique")
+    for seed, (rows, nbr, edges) in enumerate([(101, 157, 1001), (113, 1987, 2305), (5, 9, 0)]):
+        row_ptr, col, _ = _graph(seed, rows, edges, torch.int32)
+        if nbr != rows:
+            torch.manual_seed(seed)
+            from wholegraph_b200.test_utils.test_comm import gen_csr_graph
+            row_ptr, col, _ = gen_csr_graph(rows, edges, nbr, csr_row_dtype=torch.int32, csr_col_dtype=torch.int32)
+        want_row, want_col = loop.host_add_csr_self_loop(row_ptr.to(torch.int32), col)
+        rp = row_ptr.numpy().astype(np.int64)
+        exp_row = rp + np.arange(rows + 1)
+        assert want_row.numpy().tolist() == exp_row.tolist()
+        for r in range(rows):
+            seg = want_col.numpy()[exp_row[r]:exp_row[r + 1]]
+            assert seg[0] == r and np.array_equal(seg[1:], col.numpy()[rp[r]:rp[r + 1]])
+    g = torch.Generator().manual_seed(3)
+    for t, n, dt in ((10, 104, torch.int32), (113, 1987, torch.int64)):
+        targets = torch.randperm(n, generator=g, dtype=dt)[:t]
+        neighbors = torch.randint(0, n, (n,), generator=g, dtype=dt)
+        exp_uniq, exp_map = ours._first_occurrence_reference(targets.tolist(), neighbors.tolist())
+        # the reference test accepts any order of the appended part: set equality + a mapping consistent with the list
+        assert sorted(exp_uniq) == torch.unique(torch.cat((targets, neighbors))).tolist()
+        want_map = uniq.host_neighbor_raw_to_unique(torch.tensor(exp_uniq, dtype=dt), neighbors)
+        assert want_map.dtype == torch.int32 and want_map.tolist() == exp_map
