@@ -3,7 +3,6 @@
 helpers, and with them EVERY Python test module of the reference imports unchanged against this implementation.
 CPU only; the comparison needs the reference tree (skipped where /root/reference is absent)."""
 import glob
-import importlib.util
 import os
 import subprocess
 import sys
@@ -19,14 +18,10 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(REF_PY), reason="referenc
 
 def _helper_pair():
     """(this repo's test_comm, the reference's test_comm loaded from its file with its imports resolved by compat/)"""
-    for p in (ROOT, os.path.join(ROOT, "compat")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    from compat_loader import activate_compat, load_reference_file
+    activate_compat()
     import pylibwholegraph.test_utils.test_comm as ours
-    spec = importlib.util.spec_from_file_location("_reference_test_comm", os.path.join(REF_PY, "test_utils", "test_comm.py"))
-    ref = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ref)
-    return ours, ref
+    return ours, load_reference_file(os.path.join(REF_PY, "test_utils", "test_comm.py"), "_reference_test_comm")
 
 
 @needs_reference

@@ -9,7 +9,6 @@ compat/ import alias and their models are run on CPU against the oracle:
       ==  oracle (C restatement of the reference's device kernels)
 
 CPU only; skipped where /root/reference is absent."""
-import importlib.util
 import os
 import sys
 
@@ -23,13 +22,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF_OPS), reason="reference tr
 
 
 def _load(name):
-    for p in (ROOT, os.path.join(ROOT, "compat")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(REF_OPS, name + ".py"))
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
-    return m
+    from compat_loader import load_reference_file
+    return load_reference_file(os.path.join(REF_OPS, name + ".py"), "_ref_" + name)
 
 
 def _graph(seed, nodes, edges, col_dtype, weight_dtype=torch.float32):
