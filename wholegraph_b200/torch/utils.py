@@ -59,8 +59,10 @@ def str_to_wmb_wholememory_distributed_backend_type(str_wmb_type):
 
 
 def wholememory_distributed_backend_type_to_str(wmb_type):
-    return {wmb.WholeMemoryDistributedBackend.DbNCCL: "nccl",
-            wmb.WholeMemoryDistributedBackend.DbNVSHMEM: "nvshmem"}[wmb.WholeMemoryDistributedBackend(wmb_type)]
+    names = {int(wmb.WholeMemoryDistributedBackend.DbNCCL): "nccl", int(wmb.WholeMemoryDistributedBackend.DbNVSHMEM): "nvshmem"}
+    if int(wmb_type) not in names:
+        raise ValueError("WholeMemory distributed backend %s has no name, should be (DbNCCL, DbNVSHMEM)" % (wmb_type,))
+    return names[int(wmb_type)]
 
 
 def str_to_wmb_wholememory_access_type(str_access):
