@@ -1,4 +1,5 @@
 """Load modules of the reference tree, unchanged, with their `pylibwholegraph...` imports resolved by compat/ (test helper)."""
+import importlib
 import importlib.util
 import os
 import sys
@@ -22,9 +23,14 @@ def activate_compat():
     return ours
 
 
-def load_reference_file(path, name):
-    """Execute one .py file of the reference tree as module `name` (not registered in sys.modules)."""
+def load_reference_file(path, name, package=None):
+    """Execute one .py file of the reference tree as module `name` (not registered in sys.modules).  `package` (e.g.
+    "pylibwholegraph.torch") gives the file's relative imports their parent: `from .utils import x` then resolves to the
+    aliased module of this repo."""
     activate_compat()
+    if package:
+        importlib.import_module(package)
+        name = package + "." + name
     spec = importlib.util.spec_from_file_location(name, path)
     module = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(module)

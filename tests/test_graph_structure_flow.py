@@ -3,6 +3,9 @@
 seeds are the LAST target layer; hop h from the seeds uses fan-out max_neighbors[h] and seed random_seed + (hops-1-h); every
 layer's targets are a prefix of the next lower layer's; csr_row_ptr / csr_col_ind / edge_indice of a layer describe the
 sampled block between that layer's centers (rows) and its frontier (columns)."""
+import os
+
+import pytest
 import torch
 
 import wholegraph_b200.torch as wgth
@@ -69,3 +72,33 @@ def test_multilayer_sampling_bookkeeping(monkeypatch):
     calls.clear()
     g.multilayer_sample_without_replacement(seeds, fanout)
     assert [c[2] for c in calls] == [None, None]
+
+
+REF_GS = "/root/reference/python/pylibwholegraph/pylibwholegraph/torch/graph_structure.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GS), reason="reference tree not present")
+@pytest.mark.parametrize("fanout", [[3, 2], [2], [1, 4, 2]])
+def test_multilayer_bookkeeping_equals_the_reference_class(monkeypatch, fanout):
+    """The reference's GraphStructure (graph_structure.py loaded unchanged; its `from . import graph_ops, wholegraph_ops`
+    resolve to this repo's modules through compat/) and this repo's, on the same stand-in ops: identical layer lists."""
+    from compat_loader import load_reference_file
+    ref_mod = load_reference_file(REF_GS, "_reference_graph_structure", package="pylibwholegraph.torch")
+    calls = []
+    monkeypatch.setattr(gs_mod.wholegraph_ops, "unweighted_sample_without_replacement", _fake_one_hop(calls))
+    monkeypatch.setattr(gs_mod.graph_ops, "append_unique", _fake_append_unique)
+    assert ref_mod.wholegraph_ops is gs_mod.wholegraph_ops and ref_mod.graph_ops is gs_mod.graph_ops  # one set of (patched) ops
+    holder = type("T", (), {"wmb_tensor": None})()
+    seeds = torch.tensor([4, 0, 7, 9])
+    results = []
+    for cls in (wgth.GraphStructure, ref_mod.GraphStructure):
+        g = cls()
+        g.csr_row_ptr = g.csr_col_ind = holder
+        results.append(g.multilayer_sample_without_replacement(seeds, fanout))
+    ours, ref = results
+    for a, b in zip(ours, ref):                      # target_gids, edge_indice, csr_row_ptr, csr_col_ind
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and torch.equal(x, y)
+    per_class = len(calls) // 2
+    assert [c[:2] for c in calls[:per_class]] == [c[:2] for c in calls[per_class:]]  # same centers and fan-out at every hop

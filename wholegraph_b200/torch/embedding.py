@@ -151,7 +151,9 @@ class WholeMemoryEmbedding(object):
         self.adjust_cache = bool(adjust_cache) and self.wmb_cache_policy is not None
 
     def need_grad(self):
-        return self.wmb_optimizer is not None
+        """True for any live embedding, exactly like the reference (embedding.py:276-277): whether a backward pass really
+        reaches add_gradients is decided by dummy_input.requires_grad, which only WholeMemoryOptimizer.add_embedding sets."""
+        return self.wmb_embedding is not None
 
     def gather(self, indice: torch.Tensor, *, is_training: bool = False, force_dtype: Union[torch.dtype, None] = None):
         """rows[i, :] = table[indice[i], :] on the current CUDA device; with is_training and an optimizer attached the
