@@ -46,6 +46,9 @@ def test_public_names_enums_and_methods(rwmb):
         elif isinstance(theirs, type):
             missing = [m for m in dir(theirs) if not m.startswith("_") and not hasattr(ours, m)]
             assert missing == [], (n, missing)
+            # protocol methods callers rely on (e.g. comm.py broadcasts the id through uid.__dlpack__())
+            protocols = [m for m in ("__dlpack__", "__dlpack_device__", "__len__") if hasattr(theirs, m) and not hasattr(ours, m)]
+            assert protocols == [], (n, protocols)
 
 
 class _Ctx(object):

@@ -183,6 +183,17 @@ class PyWholeMemoryUniqueID:
         t._wm_keepalive = self
         return t
 
+    # The reference class exports its 128 bytes as an int8 [128] host DLPack tensor and through the buffer protocol
+    # (pyx:1022-1067); pylibwholegraph/torch/comm.py broadcasts the id through `from_dlpack(uid.__dlpack__())`.
+    def __dlpack__(self, stream=None):
+        return self.as_tensor().__dlpack__()
+
+    def __dlpack_device__(self):
+        return (1, 0)  # kDLCPU
+
+    def __buffer__(self, flags):
+        return memoryview((ctypes.c_int8 * len(self)).from_address(ctypes.addressof(self.c)))
+
 
 def create_unique_id():
     uid = PyWholeMemoryUniqueID()
@@ -827,6 +838,10 @@ class PyWholeMemoryFlattenDlpack:
             self._view, off = views[target_rank], offs[target_rank]
         self.typestr = get_type_string(data_type)
         return self._view.numel(), off
+
+    def __len__(self):
+        """element count of the current view (reference pyx:1215-1216)"""
+        return int(self._view.numel()) if self._view is not None else 0
 
     def __dlpack__(self, stream=None):
         return self._view.__dlpack__() if stream is None else self._view.__dlpack__(stream=stream)
