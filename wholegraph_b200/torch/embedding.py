@@ -258,6 +258,11 @@ def create_embedding_from_filelist(comm: WholeMemoryCommunicator, memory_type: s
     if isinstance(filelist, str):
         filelist = [filelist]
     assert last_dim_size > 0
+    # the same two rules as create_embedding, applied here as well because the file load below takes round_robin_size too
+    if embedding_entry_partition is not None and cache_policy is not None:
+        embedding_entry_partition = None
+    if embedding_entry_partition is not None:
+        round_robin_size = 0
     row_bytes = torch.tensor([], dtype=dtype).element_size() * last_dim_size
     total_bytes = 0
     for filename in filelist:
