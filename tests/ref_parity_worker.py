@@ -28,21 +28,6 @@ CASES = [
     ("continuous", "cpu", O.DT_FLOAT, O.DT_FLOAT, 64, 64, np.int64, 3000),   # reference: sorted-ids branch (row <= 512 B)
     ("chunked", "cpu", O.DT_HALF, O.DT_FLOAT, 300, 304, np.int32, 1200),
 ]
-# WG_PARITY_EXTRA=1 (tests/test_zz_ref_parity_bf16_gpu.py): bf16 on either side, which the 13 cases above do not touch, plus the
-# double -> bf16 two-hop conversion (double -> float -> bf16, the reference's type_caster chain) and wide / one-column rows
-EXTRA_CASES = [
-    ("continuous", "cuda", O.DT_BF16, O.DT_BF16, 128, 128, np.int64, 2000),
-    ("chunked", "cuda", O.DT_FLOAT, O.DT_BF16, 127, 128, np.int32, 1500),
-    ("continuous", "cuda", O.DT_BF16, O.DT_FLOAT, 33, 40, np.int64, 1500),
-    ("chunked", "cuda", O.DT_DOUBLE, O.DT_BF16, 19, 19, np.int64, 900),
-    ("continuous", "cuda", O.DT_BF16, O.DT_HALF, 64, 64, np.int32, 900),
-    ("chunked", "cuda", O.DT_HALF, O.DT_BF16, 1, 1, np.int64, 700),
-    ("continuous", "cuda", O.DT_BF16, O.DT_DOUBLE, 9, 16, np.int64, 700),
-    ("distributed", "cuda", O.DT_BF16, O.DT_BF16, 2048, 2048, np.int64, 300),
-    ("chunked", "cpu", O.DT_BF16, O.DT_FLOAT, 300, 304, np.int32, 600),
-]
-if os.environ.get("WG_PARITY_EXTRA") == "1":
-    CASES = EXTRA_CASES
 ROWS = 6007
 if os.environ.get("WG_GOLDEN_SMALL"):  # tools/make_golden.sh: a compact version of the same cases, small enough to commit
     ROWS = 307
