@@ -32,6 +32,8 @@ try:
     raise SystemExit("out-of-scope module unexpectedly importable")
 except ModuleNotFoundError:
     pass
+import pylibwholegraph
+assert isinstance(pylibwholegraph.__git_commit__, str) and isinstance(pylibwholegraph.__version__, str) and pylibwholegraph.__version__  # the reference's test_version.py
 print("compat ok")
 """
 
