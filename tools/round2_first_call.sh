@@ -10,7 +10,7 @@ step() { echo "=== $*"; }
 step "1. full GPU suite (incl. tests/test_zz_*: native env, reference-binary optimizer + graph-ops parity, full-size configs)"
 timeout 1500 python -X faulthandler -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$R.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_$R.log | cut -c1-300
 # if -x stopped early, still learn what the new files do on their own
-for f in tests/test_zz_cpp_abi.py tests/test_zz_native_env.py tests/test_zz_ref_optimizer_parity_gpu.py tests/test_zz_ref_graph_ops_parity_gpu.py tests/test_zz_ref_sampling_parity_gpu.py tests/test_zz_reference_binding_full_gpu.py tests/test_zz_vec32_gather_gpu.py tests/test_zz_training_autograd_gpu.py tests/test_zz_file_io_grid_gpu.py tests/test_zz_sampling_grid_gpu.py tests/test_zz_gather_scatter_functors_gpu.py tests/test_zz_baseline_configs_gpu.py; do
+for f in tests/test_zz_cpp_abi.py tests/test_zz_native_env.py tests/test_zz_ref_optimizer_parity_gpu.py tests/test_zz_ref_graph_ops_parity_gpu.py tests/test_zz_ref_sampling_parity_gpu.py tests/test_zz_reference_binding_full_gpu.py tests/test_zz_vec32_gather_gpu.py tests/test_zz_training_autograd_gpu.py tests/test_zz_file_io_grid_gpu.py tests/test_zz_sampling_grid_gpu.py tests/test_zz_gather_scatter_functors_gpu.py tests/test_zz_one_dim_table_gpu.py tests/test_zz_baseline_configs_gpu.py; do
   timeout 900 python -X faulthandler -m pytest $f -m gpu -q -s > gpurun_out/$(basename $f .py)_$R.log 2>&1; echo "$f rc=$?"; grep -E "bit-identical|passed|failed|Error" gpurun_out/$(basename $f .py)_$R.log | tail -6 | cut -c1-300
 done
 
