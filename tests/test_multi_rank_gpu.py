@@ -28,7 +28,9 @@ def _run(world, scenario, env=None, share_gpu=False):
     ctx = mp.get_context("spawn")
     results = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=S.worker, args=(r, world, port, ngpus, scenario, env or {}, results)) for r in range(world)]
+    # a rank that diverges must end in an error, not park its peers in a collective until the join below gives up
+    env = dict({"WG_BOOTSTRAP_TIMEOUT_S": "300"}, **(env or {}))
+    procs = [ctx.Process(target=S.worker, args=(r, world, port, ngpus, scenario, env, results)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

@@ -27,12 +27,13 @@ constexpr int kConnectTimeoutMs = 120000;
 
 /* A collective whose peer never answers (a rank that died without closing its socket cannot happen on one box, but a
  * rank that took a different code path can) must end in an error, not in a hang: every blocking receive gives up after
- * WG_BOOTSTRAP_TIMEOUT_S seconds (default 1800; 0 = wait forever). */
+ * WG_BOOTSTRAP_TIMEOUT_S seconds when that variable is set.  Default: wait forever, like the reference's NCCL control plane --
+ * a rank may legitimately sit in a barrier for a long time while another one loads a dataset. */
 int recv_timeout_ms()
 {
   static const int ms = [] {
     const char* v = getenv("WG_BOOTSTRAP_TIMEOUT_S");
-    long s        = (v && *v) ? atol(v) : 1800;
+    long s        = (v && *v) ? atol(v) : 0;
     if (s <= 0) return -1;
     return (int)std::min<long>(s, 2000000) * 1000;
   }();
