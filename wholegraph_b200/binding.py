@@ -449,14 +449,14 @@ def store_wholememory_handle_to_file(wholememory_handle_int_ptr, memory_offset, 
 
 class PyWholeMemoryTensorDescription:
     def __init__(self):
+        # all-zero like the reference class (pyx:1438-1441): dim 0, dtype unknown, sizes / strides unset until the setters run
         self.tensor_description = _lib.TensorDescription()
-        lib.wholememory_initialize_tensor_desc(byref(self.tensor_description))
 
     def set_dtype(self, dtype):
         self.tensor_description.dtype = int(dtype)
 
     def set_shape(self, shape):
-        assert 0 < len(shape) <= _lib.WHOLEMEMORY_MAX_TENSOR_DIM
+        assert 0 < len(shape) < _lib.WHOLEMEMORY_MAX_TENSOR_DIM  # 1..7 dims, like the reference class (pyx:1450)
         self.tensor_description.dim = len(shape)
         for i, s in enumerate(shape):
             self.tensor_description.sizes[i] = int(s)
@@ -494,7 +494,8 @@ class WrappedLocalTensor:
         self.wm_tensor = c_void_p(None)
 
     def __del__(self):
-        if getattr(self, "wm_tensor", None) is not None and self.wm_tensor.value:
+        # (module globals are already cleared when this runs at interpreter shutdown: nothing left to free then)
+        if lib is not None and getattr(self, "wm_tensor", None) is not None and self.wm_tensor.value:
             lib.wholememory_destroy_tensor(self.wm_tensor)
             self.wm_tensor = c_void_p(None)
 
