@@ -17,7 +17,14 @@ _comm = None
 
 
 def single_comm():
+    """The world_size-1 communicator the single-process GPU tests share.  Re-created when something finalized the
+    library in between (wholememory_finalize destroys every communicator; a stale one is refused with INVALID_INPUT)."""
     global _comm
+    if _comm is not None:
+        try:
+            _comm.get_rank()
+        except Exception:
+            _comm = None
     if _comm is None:
         wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
         torch.cuda.set_device(0)

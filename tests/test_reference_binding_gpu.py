@@ -118,4 +118,8 @@ def test_reference_cython_binding_on_our_library():
 
     assert rwmb.py_get_wholememory_tensor_count() >= 0
     rwmb.destroy_communicator(comm)
-    rwmb.finalize()
+    # No rwmb.finalize() here: the reference module is linked to the SAME libwholegraph.so the ctypes binding has open, and
+    # wholememory_finalize destroys every communicator of the process (reference initialize.cpp:73-77) -- including the one
+    # tests/gpu_utils.py shares across test files.  (Round 1's GPU suite died of exactly that; the library now also refuses
+    # stale handles, tests/test_stale_handles.py.)  finalize() through the reference binding is exercised in a process of
+    # its own by tests/ref_binding_worker.py.

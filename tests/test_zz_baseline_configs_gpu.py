@@ -18,8 +18,7 @@ import torch
 
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

@@ -31,7 +31,6 @@ def test_cpp_caller_host_side(program):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")
 @pytest.mark.parametrize("ranks", [1, 2])
 def test_cpp_caller_on_the_gpu(program, ranks):
     env = dict(os.environ, WG_BOOTSTRAP_TIMEOUT_S="120")  # a diverged rank must end in an error well before the pytest timeout

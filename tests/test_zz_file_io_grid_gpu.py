@@ -6,8 +6,7 @@ CONTINUOUS / CHUNKED / DISTRIBUTED, device and host memory.  One rank, and 2 / 3
 tests/test_multi_rank_gpu.py.)"""
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.timeout(900)

@@ -6,8 +6,7 @@ One rank and two ranks sharing the GPU.
 tests/test_gather_scatter_gpu.py and the `gather_scatter` scenario of tests/test_multi_rank_gpu.py.)"""
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.timeout(900)

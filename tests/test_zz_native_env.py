@@ -108,7 +108,6 @@ def test_python_callbacks_unaffected_after_unload():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")
 def test_native_env_matches_python_callbacks_on_gpu():
     import os
     import subprocess

@@ -7,8 +7,7 @@ accepts, is covered by the verified test_gather_scatter_gpu.py; the [n, 1] form 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("mem_type", ["continuous", "chunked", "distributed"])

@@ -6,8 +6,7 @@ combinations of the optional outputs, checked against the oracle.  One rank and 
 `weighted_sampling` scenarios of tests/test_multi_rank_gpu.py.)"""
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.timeout(900)

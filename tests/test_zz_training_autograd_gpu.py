@@ -9,8 +9,7 @@ import torch
 
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("kind,params", [("sgd", {}), ("adam", {}), ("adagrad", {"epsilon": 1e-6}), ("rmsprop", {"alpha": 0.9})])

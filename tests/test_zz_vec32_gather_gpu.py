@@ -11,8 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution pending: written after the round-1 GPU budget was spent; remove this marker once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -102,6 +102,7 @@ static wholememory_comm_t create_comm(const wholememory_unique_id_t& uid, int ra
   std::lock_guard<std::mutex> lk(g_comm_mu);
   c->comm_id         = g_next_comm_id++;
   g_comms[c->comm_id] = c;
+  obj_register(OBJ_COMM, c);
   WM_DEBUG("communicator %d: rank %d/%d dev %d peer_capable=%d granularity=%zu",
            c->comm_id, rank, size, c->dev_id, (int)c->all_peer_capable, c->alloc_granularity);
   return c;
@@ -109,6 +110,7 @@ static wholememory_comm_t create_comm(const wholememory_unique_id_t& uid, int ra
 
 static void destroy_comm(wholememory_comm_t c)
 {
+  obj_unregister(OBJ_COMM, c); /* first: from here on every entry point refuses this communicator */
   {
     std::lock_guard<std::mutex> lk(c->mu);
     /* reference communicator.cpp:808-827: a dying communicator takes its memory with it */
@@ -193,7 +195,8 @@ wholememory_error_code_t wholememory_split_communicator(wholememory_comm_t* new_
                                                         int key)
 {
   return wm::guarded("wholememory_split_communicator", [&]() -> wholememory_error_code_t {
-    if (new_comm == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    if (new_comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(comm);
     std::unique_lock<std::mutex> lk(comm->mu);
     struct ck {
       int32_t color, key, rank;
@@ -230,7 +233,7 @@ wholememory_error_code_t wholememory_split_communicator(wholememory_comm_t* new_
 wholememory_error_code_t wholememory_destroy_communicator(wholememory_comm_t comm)
 {
   return wm::guarded("wholememory_destroy_communicator", [&]() -> wholememory_error_code_t {
-    if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(comm);
     wm::destroy_comm(comm);
     return WHOLEMEMORY_SUCCESS;
   });
@@ -239,7 +242,7 @@ wholememory_error_code_t wholememory_destroy_communicator(wholememory_comm_t com
 wholememory_error_code_t wholememory_communicator_support_type_location(
   wholememory_comm_t comm, wholememory_memory_type_t memory_type, wholememory_memory_location_t memory_location)
 {
-  if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   if (memory_type != WHOLEMEMORY_MT_CONTINUOUS && memory_type != WHOLEMEMORY_MT_CHUNKED &&
       memory_type != WHOLEMEMORY_MT_DISTRIBUTED)
     return WHOLEMEMORY_NOT_SUPPORTED; /* HIERARCHY: multi-node only */
@@ -253,28 +256,32 @@ wholememory_error_code_t wholememory_communicator_support_type_location(
 
 wholememory_error_code_t wholememory_communicator_get_rank(int* rank, wholememory_comm_t comm)
 {
-  if (rank == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (rank == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   *rank = comm->world_rank;
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_communicator_get_size(int* size, wholememory_comm_t comm)
 {
-  if (size == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (size == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   *size = comm->world_size;
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_communicator_get_local_size(int* local_size, wholememory_comm_t comm)
 {
-  if (local_size == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (local_size == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   *local_size = comm->world_size; /* single box: every rank is local */
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_communicator_get_clique_info(clique_info_t* clique_info, wholememory_comm_t comm)
 {
-  if (clique_info == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (clique_info == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   /* no MNNVL fabric on an HGX box: same answer the reference gives for a zero cluster uuid
    * (communicator.cpp:541-547) */
   *clique_info              = clique_info_t{};
@@ -287,7 +294,7 @@ bool wholememory_communicator_is_bind_to_nvshmem(wholememory_comm_t) { return fa
 wholememory_error_code_t wholememory_communicator_set_distributed_backend(
   wholememory_comm_t comm, wholememory_distributed_backend_t distributed_backend)
 {
-  if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(comm);
   if (distributed_backend == WHOLEMEMORY_DB_NVSHMEM) {
     WM_ERROR("NVSHMEM backend is not part of this build (no multi-backend dispatch)");
     return WHOLEMEMORY_NOT_SUPPORTED;
@@ -298,13 +305,13 @@ wholememory_error_code_t wholememory_communicator_set_distributed_backend(
 
 wholememory_distributed_backend_t wholememory_communicator_get_distributed_backend(wholememory_comm_t comm)
 {
-  return comm ? comm->distributed_backend : WHOLEMEMORY_DB_NONE;
+  return wm::live(comm) ? comm->distributed_backend : WHOLEMEMORY_DB_NONE;
 }
 
 wholememory_error_code_t wholememory_communicator_barrier(wholememory_comm_t comm)
 {
   return wm::guarded("wholememory_communicator_barrier", [&]() -> wholememory_error_code_t {
-    if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(comm);
     /* The reference barrier (nccl_comms.cpp:82-86 + sync) only orders its own stream.  Here the
      * rendezvous is on the host, so first drain this rank's device: once every rank has passed
      * the barrier, all peer stores issued before it (scatter into mapped memory) are visible. */

@@ -252,6 +252,7 @@ wholememory_error_code_t wholememory_create_embedding_optimizer(wholememory_embe
       WM_ERROR("unknown optimizer type %d", (int)optimizer_type);
       return WHOLEMEMORY_NOT_IMPLEMENTED; /* reference embedding_optimizer.cpp:527 */
   }
+  wm::obj_register(wm::OBJ_OPTIMIZER, o);
   *optimizer = o;
   return WHOLEMEMORY_SUCCESS;
 }
@@ -260,7 +261,8 @@ wholememory_error_code_t wholememory_optimizer_set_parameter(wholememory_embeddi
                                                              const char* parameter_name,
                                                              void* value)
 {
-  if (optimizer == nullptr || parameter_name == nullptr || value == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (parameter_name == nullptr || value == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_KNOWN(wm::OBJ_OPTIMIZER, optimizer);
   const float v      = *static_cast<const float*>(value);
   const std::string k = parameter_name;
   auto& p            = optimizer->params;
@@ -280,7 +282,12 @@ wholememory_error_code_t wholememory_optimizer_set_parameter(wholememory_embeddi
   return WHOLEMEMORY_SUCCESS;
 }
 
-void wholememory_destroy_embedding_optimizer(wholememory_embedding_optimizer_t optimizer) { delete optimizer; }
+void wholememory_destroy_embedding_optimizer(wholememory_embedding_optimizer_t optimizer)
+{
+  if (!wm::obj_known(wm::OBJ_OPTIMIZER, optimizer)) return; /* null, or destroyed twice */
+  wm::obj_unregister(wm::OBJ_OPTIMIZER, optimizer);
+  delete optimizer;
+}
 
 wholememory_error_code_t wholememory_create_embedding_cache_policy(wholememory_embedding_cache_policy_t* cache_policy,
                                                                    wholememory_comm_t cache_level_comm,
@@ -295,11 +302,15 @@ wholememory_error_code_t wholememory_create_embedding_cache_policy(wholememory_e
     return WHOLEMEMORY_INVALID_VALUE;
   }
   *cache_policy = new wholememory_embedding_cache_policy_{cache_level_comm, memory_type, memory_location, access_type, cache_ratio};
+  wm::obj_register(wm::OBJ_CACHE_POLICY, *cache_policy);
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_destroy_embedding_cache_policy(wholememory_embedding_cache_policy_t cache_policy)
 {
+  if (cache_policy == nullptr) return WHOLEMEMORY_SUCCESS; /* deleting nothing succeeds, as with the reference's plain delete */
+  WM_REQUIRE_KNOWN(wm::OBJ_CACHE_POLICY, cache_policy);
+  wm::obj_unregister(wm::OBJ_CACHE_POLICY, cache_policy);
   delete cache_policy;
   return WHOLEMEMORY_SUCCESS;
 }
@@ -315,7 +326,9 @@ wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* w
                                                       int round_robin_size)
 {
   return wm::guarded("wholememory_create_embedding", [&]() -> wholememory_error_code_t {
-    if (wholememory_embedding == nullptr || embedding_tensor_description == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    if (wholememory_embedding == nullptr || embedding_tensor_description == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(comm);
+    if (cache_policy != nullptr) WM_REQUIRE_KNOWN(wm::OBJ_CACHE_POLICY, cache_policy);
     wholememory_matrix_description_t md;
     if (!wholememory_convert_tensor_desc_to_matrix(&md, embedding_tensor_description) || embedding_tensor_description->dim != 2) {
       WM_ERROR("wholememory_create_embedding input description must be 2D matrix");
@@ -345,6 +358,7 @@ wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* w
       (void)wholememory_destroy_tensor(e->allocated); /* collective like the creation: every rank takes this branch */
       return rc;
     }
+    wm::obj_register(wm::OBJ_EMBEDDING, e.get());
     *wholememory_embedding = e.release();
     return WHOLEMEMORY_SUCCESS;
   });
@@ -353,27 +367,35 @@ wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* w
 wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t e)
 {
   return wm::guarded("wholememory_destroy_embedding", [&]() -> wholememory_error_code_t {
-    if (e == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_KNOWN(wm::OBJ_EMBEDDING, e);
+    /* an embedding whose communicator is gone (wholememory_finalize) has lost its memory already: the tensor
+     * objects below skip the collective free and only the host-side objects are released */
     wm::destroy_states(e);
-    wm::destroy_push_stage(&e->grad_stage);
+    if (wm::live(e->comm)) wm::destroy_push_stage(&e->grad_stage);
     if (e->user) wholememory_destroy_tensor(e->user);
     if (e->allocated) WHOLEMEMORY_RETURN_ON_FAIL(wholememory_destroy_tensor(e->allocated));
+    wm::obj_unregister(wm::OBJ_EMBEDDING, e);
     delete e;
     return WHOLEMEMORY_SUCCESS;
   });
 }
 
-wholememory_tensor_t wholememory_embedding_get_embedding_tensor(wholememory_embedding_t e) { return e ? e->user : nullptr; }
+wholememory_tensor_t wholememory_embedding_get_embedding_tensor(wholememory_embedding_t e)
+{
+  return wm::obj_known(wm::OBJ_EMBEDDING, e) ? e->user : nullptr;
+}
 
 wholememory_error_code_t wholememory_embedding_set_optimizer(wholememory_embedding_t e, wholememory_embedding_optimizer_t optimizer)
 {
   return wm::guarded("wholememory_embedding_set_optimizer", [&]() -> wholememory_error_code_t {
-    if (e == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_KNOWN(wm::OBJ_EMBEDDING, e);
+    WM_REQUIRE_LIVE(e->comm);
     if (e->optimizer != nullptr) {
       WM_ERROR("optimizer can only be set once.");
       return WHOLEMEMORY_NOT_SUPPORTED;
     }
     if (optimizer == nullptr) return WHOLEMEMORY_SUCCESS;
+    WM_REQUIRE_KNOWN(wm::OBJ_OPTIMIZER, optimizer);
     if (e->dtype != WHOLEMEMORY_DT_FLOAT) {
       WM_ERROR("Only float embedding supports training.");
       return WHOLEMEMORY_NOT_IMPLEMENTED;
@@ -390,7 +412,7 @@ wholememory_error_code_t wholememory_embedding_gather(wholememory_embedding_t e,
                                                       wholememory_env_func_t* p_env_fns,
                                                       int64_t stream_int)
 {
-  if (e == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_KNOWN(wm::OBJ_EMBEDDING, e);
   /* the padded table is gathered, not the user view (reference noncached_embedding::gather, :553-562):
    * the output has D columns, so only the first D of each padded row are read. */
   return wholememory_gather(e->user, indices, output, p_env_fns, reinterpret_cast<void*>(stream_int), e->gather_sms);
@@ -405,7 +427,11 @@ wholememory_error_code_t wholememory_embedding_gather_gradient_apply(wholememory
                                                                      int64_t stream_int)
 {
   return wm::guarded("wholememory_embedding_gather_gradient_apply", [&]() -> wholememory_error_code_t {
-    if (e == nullptr || indices == nullptr || grads == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_KNOWN(wm::OBJ_EMBEDDING, e);
+    WM_REQUIRE_LIVE(e->allocated);
+    WM_REQUIRE_LIVE(indices);
+    WM_REQUIRE_LIVE(grads);
+    if (e->optimizer != nullptr) WM_REQUIRE_KNOWN(wm::OBJ_OPTIMIZER, e->optimizer);
     return wm::gradient_apply(e, indices, grads, lr, p_env_fns, reinterpret_cast<cudaStream_t>(stream_int));
   });
 }
@@ -413,13 +439,13 @@ wholememory_error_code_t wholememory_embedding_gather_gradient_apply(wholememory
 const char* const* wholememory_embedding_get_optimizer_state_names(wholememory_embedding_t e)
 {
   static const char* const none[] = {nullptr};
-  if (e == nullptr || e->optimizer == nullptr) return none;
+  if (!wm::obj_known(wm::OBJ_EMBEDDING, e) || !wm::obj_known(wm::OBJ_OPTIMIZER, e->optimizer)) return none;
   return e->optimizer->state_names.data();
 }
 
 wholememory_tensor_t wholememory_embedding_get_optimizer_state(wholememory_embedding_t e, const char* name)
 {
-  if (e == nullptr || name == nullptr) return nullptr;
+  if (!wm::obj_known(wm::OBJ_EMBEDDING, e) || name == nullptr) return nullptr;
   for (auto& kv : e->named_states)
     if (kv.first == name) return kv.second;
   WM_ERROR("optimizer state name %s not found", name);
@@ -428,12 +454,12 @@ wholememory_tensor_t wholememory_embedding_get_optimizer_state(wholememory_embed
 
 wholememory_error_code_t wholememory_embedding_writeback_cache(wholememory_embedding_t e, int64_t)
 {
-  return e ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
+  return wm::obj_known(wm::OBJ_EMBEDDING, e) ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
 }
 
 wholememory_error_code_t wholememory_embedding_drop_all_cache(wholememory_embedding_t e, int64_t)
 {
-  return e ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
+  return wm::obj_known(wm::OBJ_EMBEDDING, e) ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
 }
 
 } /* extern "C" */

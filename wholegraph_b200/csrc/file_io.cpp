@@ -20,7 +20,7 @@ constexpr size_t kStageBytes = 16u << 20;
 
 wholememory_error_code_t check_layout(wholememory_handle_t h, size_t memory_offset, size_t stride, size_t entry_size)
 {
-  if (h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   if (entry_size == 0 || memory_offset + entry_size > stride) { /* reference file_io.cpp:1868-1874 */
     WM_ERROR("Invalid input, entry_size=%zu, memory_entry_stride=%zu, memory_offset=%zu", entry_size, stride, memory_offset);
     return WHOLEMEMORY_INVALID_INPUT;

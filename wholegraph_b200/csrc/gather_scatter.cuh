@@ -201,7 +201,16 @@ __device__ __forceinline__ char* shfl_ptr(char* p, int src_lane)
  * Within a batch, lane l < R resolves row l; then the R*V vectors of the batch are walked by all
  * lanes, UNROLL at a time (loads first, then stores).
  */
-template <typename IdxT, int VEC, bool GATHER, int UNROLL>
+/* programmatic dependent launch (sm_90+): when the kernel is launched with the programmatic-stream-serialization
+ * attribute, the NEXT grid in the stream may start being scheduled as soon as every CTA of this one has passed
+ * pdl_launch_dependents(), and this grid's pdl_wait() returns only when the PREVIOUS grid has completed and its writes
+ * are visible.  Without the attribute both are no-ops.  Back-to-back gathers overlap their launch ramp with the
+ * predecessor's tail this way; nothing that depends on earlier work is read before pdl_wait(). */
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+/* VN_CT > 0: the row is exactly VN_CT vectors (a power of two): the unit -> (row, vector) map is a shift and a mask */
+template <typename IdxT, int VEC, bool GATHER, int UNROLL, int VN_CT = 0>
 __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
                                                           row_geom g,
                                                           const IdxT* __restrict__ indices,
@@ -215,9 +224,11 @@ __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
   const int64_t nwarps = (int64_t)gridDim.x * warps_cta;
   const int R          = g.batch_rows;
   const int64_t nbatch = (n + R - 1) / R;
-  const uint32_t Vn    = (uint32_t)g.units_per_row; /* row size in VEC units */
+  const uint32_t Vn    = VN_CT > 0 ? (uint32_t)VN_CT : (uint32_t)g.units_per_row; /* row size in VEC units */
   const uint64_t magic = g.div_magic;
 
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t batch = warp;
   /* software prefetch of the next batch's index */
   IdxT next_idx = -1;
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         uint32_t w   = w0 + (uint32_t)u * 32u + (uint32_t)lane;
-        uint32_t row = (uint32_t)(((uint64_t)w * magic) >> 40);
+        uint32_t row = VN_CT > 0 ? w / (uint32_t)VN_CT : (uint32_t)(((uint64_t)w * magic) >> 40);
         uint32_t v   = w - row * Vn;
         /* shuffles are executed by all lanes, out-of-range lanes read lane (row & 31) harmlessly */
         char* t   = shfl_ptr(trow, (int)(row & 31u));

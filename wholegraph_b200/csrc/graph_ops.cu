@@ -170,7 +170,9 @@ wholememory_error_code_t graph_append_unique(wholememory_tensor_t target_nodes_t
 {
   return wm::guarded("graph_append_unique", [&]() -> wholememory_error_code_t {
     using namespace wm;
-    if (!target_nodes_tensor || !neighbor_nodes_tensor) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(target_nodes_tensor);
+    WM_REQUIRE_LIVE(neighbor_nodes_tensor);
+    if (output_neighbor_raw_to_unique_mapping_tensor != nullptr) WM_REQUIRE_LIVE(output_neighbor_raw_to_unique_mapping_tensor);
     /* argument checks in the reference's order and with its codes (graph_ops/append_unique.cpp:28-72) ... */
     if (!is_1d(target_nodes_tensor)) {
       WM_ERROR("target_nodes_tensor should be 1D tensor.");
@@ -238,8 +240,7 @@ wholememory_error_code_t csr_add_self_loop(wholememory_tensor_t csr_row_ptr_tens
   return wm::guarded("csr_add_self_loop", [&]() -> wholememory_error_code_t {
     using namespace wm;
     wholememory_tensor_t ts[4] = {csr_row_ptr_tensor, csr_col_ptr_tensor, output_csr_row_ptr_tensor, output_csr_col_ptr_tensor};
-    for (auto t : ts)
-      if (t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    for (auto t : ts) WM_REQUIRE_LIVE(t);
     /* argument checks in the reference's order and with its codes (graph_ops/csr_add_self_loop.cpp:26-87): rank and dtype
      * of each tensor in turn (INVALID_INPUT), then "views as an array" for each (LOGIC_ERROR) ... */
     for (auto t : ts) {

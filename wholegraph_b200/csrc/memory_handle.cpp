@@ -320,8 +320,9 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
                                        size_t granularity,
                                        size_t* rank_entry_partition)
 {
-  if (out == nullptr || comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (out == nullptr) return WHOLEMEMORY_INVALID_INPUT;
   *out = nullptr;
+  WM_REQUIRE_LIVE(comm);
   if (granularity == 0 || total_size % granularity != 0) return WHOLEMEMORY_INVALID_VALUE;
   if (type != WHOLEMEMORY_MT_CONTINUOUS && type != WHOLEMEMORY_MT_CHUNKED && type != WHOLEMEMORY_MT_DISTRIBUTED) {
     WM_ERROR("memory type %d is not supported by this build (HIERARCHY is multi-node only)", (int)type);
@@ -346,10 +347,19 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
 
   std::lock_guard<std::mutex> lk(comm->mu);
   /* collective sanity check (the reference's WM_COMM_CHECK_ALL_SAME, communicator.hpp:234-263) */
+  /* every entry of a custom partition must agree too (the reference checks each one); an FNV-1a hash of the array
+   * travels with the scalars, so ranks with different partitions of the same total fail here instead of building
+   * different owner tables */
+  uint64_t part_hash = 0;
+  if (rank_entry_partition != nullptr) {
+    part_hash = 1469598103934665603ull;
+    for (int r = 0; r < comm->world_size; ++r)
+      for (int b = 0; b < 8; ++b) part_hash = (part_hash ^ ((rank_entry_partition[r] >> (8 * b)) & 0xff)) * 1099511628211ull;
+  }
   struct params {
-    uint64_t total, gran;
+    uint64_t total, gran, part_hash;
     int32_t type, location, id, custom;
-  } mine{total_size, granularity, (int32_t)type, (int32_t)location, comm->next_handle_id, rank_entry_partition != nullptr};
+  } mine{total_size, granularity, part_hash, (int32_t)type, (int32_t)location, comm->next_handle_id, rank_entry_partition != nullptr};
   std::vector<params> all(comm->world_size);
   comm->boot->allgather(&mine, all.data(), sizeof(params));
   for (auto& p : all)
@@ -382,6 +392,7 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
   }
   comm->boot->barrier(); /* everyone mapped before anyone touches a peer */
   comm->handles[h->id] = h.get();
+  obj_register(OBJ_HANDLE, h.get());
   *out                 = h.release();
   return WHOLEMEMORY_SUCCESS;
 }
@@ -389,6 +400,7 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
 void destroy_handle_locked(wholememory_handle_t h)
 {
   auto* comm = h->comm;
+  obj_unregister(OBJ_HANDLE, h);
   if (comm->dev_id >= 0) (void)cudaDeviceSynchronize();
   comm->boot->barrier(); /* nobody still reads my shard */
   release_storage(h);
@@ -418,7 +430,7 @@ wholememory_error_code_t wholememory_malloc(wholememory_handle_t* wholememory_ha
 wholememory_error_code_t wholememory_free(wholememory_handle_t h)
 {
   return wm::guarded("wholememory_free", [&]() -> wholememory_error_code_t {
-    if (h == nullptr || h->comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+    WM_REQUIRE_LIVE(h);
     auto* comm = h->comm;
     std::lock_guard<std::mutex> lk(comm->mu);
     if (comm->handles.find(h->id) == comm->handles.end()) return WHOLEMEMORY_INVALID_VALUE;
@@ -429,38 +441,45 @@ wholememory_error_code_t wholememory_free(wholememory_handle_t h)
 
 wholememory_error_code_t wholememory_get_communicator(wholememory_comm_t* comm, wholememory_handle_t h)
 {
-  if (comm == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   *comm = h->comm;
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_get_local_communicator(wholememory_comm_t* comm, wholememory_handle_t h)
 {
-  if (comm == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   return WHOLEMEMORY_NOT_SUPPORTED; /* HIERARCHY only (reference memory_handle.cpp:1999-2001) */
 }
 
 wholememory_error_code_t wholememory_get_cross_communicator(wholememory_comm_t* comm, wholememory_handle_t h)
 {
-  if (comm == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (comm == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   return WHOLEMEMORY_NOT_SUPPORTED;
 }
 
-wholememory_memory_type_t wholememory_get_memory_type(wholememory_handle_t h) { return h->type; }
-wholememory_memory_location_t wholememory_get_memory_location(wholememory_handle_t h) { return h->location; }
+/* value-returning getters have no error channel: a dead handle reads as "none" / 0 */
+wholememory_memory_type_t wholememory_get_memory_type(wholememory_handle_t h) { return wm::live(h) ? h->type : WHOLEMEMORY_MT_NONE; }
+wholememory_memory_location_t wholememory_get_memory_location(wholememory_handle_t h)
+{
+  return wm::live(h) ? h->location : WHOLEMEMORY_ML_NONE;
+}
 wholememory_distributed_backend_t wholememory_get_distributed_backend(wholememory_handle_t h)
 {
-  return h->comm->distributed_backend;
+  return wm::live(h) ? h->comm->distributed_backend : WHOLEMEMORY_DB_NONE;
 }
-size_t wholememory_get_total_size(wholememory_handle_t h) { return h->total_size; }
-size_t wholememory_get_data_granularity(wholememory_handle_t h) { return h->granularity; }
+size_t wholememory_get_total_size(wholememory_handle_t h) { return wm::live(h) ? h->total_size : 0; }
+size_t wholememory_get_data_granularity(wholememory_handle_t h) { return wm::live(h) ? h->granularity : 0; }
 
 wholememory_error_code_t wholememory_get_local_memory(void** local_ptr,
                                                       size_t* local_size,
                                                       size_t* local_offset,
                                                       wholememory_handle_t h)
 {
-  if (h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   int me = h->comm->world_rank;
   if (local_ptr) *local_ptr = h->local_ptr;
   if (local_size) *local_size = h->part_sizes[me];
@@ -484,7 +503,8 @@ wholememory_error_code_t wholememory_get_rank_memory(void** rank_memory_ptr,
                                                      int rank,
                                                      wholememory_handle_t h)
 {
-  if (h == nullptr || rank < 0 || rank >= h->comm->world_size) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
+  if (rank < 0 || rank >= h->comm->world_size) return WHOLEMEMORY_INVALID_INPUT;
   /* DISTRIBUTED memory is private by contract even when this build peer-maps it internally */
   if (h->type == WHOLEMEMORY_MT_DISTRIBUTED) {
     if (rank_memory_ptr) *rank_memory_ptr = nullptr;
@@ -509,7 +529,8 @@ wholememory_error_code_t wholememory_equal_entry_partition_plan(size_t* entry_pe
 
 wholememory_error_code_t wholememory_get_global_pointer(void** global_ptr, wholememory_handle_t h)
 {
-  if (global_ptr == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (global_ptr == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   bool flat   = h->type == WHOLEMEMORY_MT_CONTINUOUS || (h->type == WHOLEMEMORY_MT_CHUNKED && h->location == WHOLEMEMORY_ML_HOST);
   *global_ptr = flat ? h->flat_base : nullptr;
   return *global_ptr ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
@@ -517,21 +538,24 @@ wholememory_error_code_t wholememory_get_global_pointer(void** global_ptr, whole
 
 wholememory_error_code_t wholememory_get_global_reference(wholememory_gref_t* gref, wholememory_handle_t h)
 {
-  if (gref == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (gref == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   *gref = h->gref;
   return gref->pointer ? WHOLEMEMORY_SUCCESS : WHOLEMEMORY_INVALID_INPUT;
 }
 
 wholememory_error_code_t wholememory_get_rank_partition_sizes(size_t* rank_mem_sizes, wholememory_handle_t h)
 {
-  if (rank_mem_sizes == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (rank_mem_sizes == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   std::copy(h->part_sizes.begin(), h->part_sizes.end(), rank_mem_sizes);
   return WHOLEMEMORY_SUCCESS;
 }
 
 wholememory_error_code_t wholememory_get_rank_partition_offsets(size_t* rank_mem_offsets, wholememory_handle_t h)
 {
-  if (rank_mem_offsets == nullptr || h == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (rank_mem_offsets == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(h);
   std::copy(h->part_offsets.begin(), h->part_offsets.end(), rank_mem_offsets);
   return WHOLEMEMORY_SUCCESS;
 }

@@ -307,8 +307,7 @@ wholememory_error_code_t wholegraph_csr_unweighted_sample_without_replacement(wh
 {
   return wm::guarded("wholegraph_csr_unweighted_sample_without_replacement", [&]() -> wholememory_error_code_t {
     using namespace wm;
-    if (!wm_csr_row_ptr_tensor || !wm_csr_col_ptr_tensor || !center_nodes_tensor || !output_sample_offset_tensor)
-      return WHOLEMEMORY_INVALID_INPUT;
+    for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, center_nodes_tensor, output_sample_offset_tensor}) WM_REQUIRE_LIVE(t);
     /* argument checks in the reference's order and with its codes (unweighted_sample_without_replacement.cpp:64-111) ... */
     if (!is_1d(wm_csr_row_ptr_tensor)) {
       WM_ERROR("wm_csr_row_ptr_tensor should be 1D tensor.");
@@ -409,7 +408,7 @@ wholememory_error_code_t wholegraph_csr_unweighted_sample_without_replacement(wh
 /* host replay of the sampler's stream (reference raft_random_gen.cu:27-71) */
 wholememory_error_code_t generate_random_positive_int_cpu(int64_t random_seed, int64_t subsequence, wholememory_tensor_t output)
 {
-  if (output == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(output);
   auto d = *wholememory_tensor_get_tensor_description(output);
   if (d.dim != 1) {
     WM_ERROR("output should be 1D tensor.");

@@ -101,7 +101,9 @@ wholememory_error_code_t prepare(wholememory_tensor_t table,
                                  bool is_gather,
                                  op_args* a)
 {
-  if (table == nullptr || indices == nullptr || dense == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(table);
+  WM_REQUIRE_LIVE(indices);
+  WM_REQUIRE_LIVE(dense);
   const wholememory_error_code_t bad_table = is_gather ? WHOLEMEMORY_LOGIC_ERROR : WHOLEMEMORY_INVALID_INPUT;
   wholememory_tensor_description_t td = *wholememory_tensor_get_tensor_description(table);
   if (td.dim != 1 && td.dim != 2) {

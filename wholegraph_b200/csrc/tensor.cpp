@@ -18,6 +18,7 @@ wholememory_tensor_t new_tensor()
   auto* t = new wholememory_tensor_();
   t->root = t;
   ++g_live_tensors;
+  wm::obj_register(wm::OBJ_TENSOR, t);
   return t;
 }
 
@@ -69,8 +70,10 @@ wholememory_error_code_t wholememory_create_tensor(wholememory_tensor_t* out,
 
 wholememory_error_code_t wholememory_destroy_tensor(wholememory_tensor_t t)
 {
-  if (t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
-  if (t->own_handle && t->is_wm) WHOLEMEMORY_RETURN_ON_FAIL(wholememory_free(t->handle));
+  WM_REQUIRE_KNOWN(wm::OBJ_TENSOR, t);
+  /* a handle that died with its communicator (wholememory_finalize) is already gone: only the tensor object is left */
+  if (t->own_handle && t->is_wm && wm::live(t->handle)) WHOLEMEMORY_RETURN_ON_FAIL(wholememory_free(t->handle));
+  wm::obj_unregister(wm::OBJ_TENSOR, t);
   --g_live_tensors;
   delete t;
   return WHOLEMEMORY_SUCCESS;
@@ -101,7 +104,8 @@ wholememory_error_code_t wholememory_make_tensor_from_handle(wholememory_tensor_
                                                              wholememory_handle_t handle,
                                                              wholememory_tensor_description_t* desc)
 {
-  if (out == nullptr || handle == nullptr || desc == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (out == nullptr || desc == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(handle);
   if (desc->dim < 1 || desc->dim > 2 || desc->strides[desc->dim - 1] != 1 || !known_dtype(desc->dtype)) {
     WM_ERROR("wholememory_make_tensor_from_handle: bad description (dim=%d dtype=%d)", desc->dim, (int)desc->dtype);
     return WHOLEMEMORY_INVALID_INPUT;
@@ -114,21 +118,23 @@ wholememory_error_code_t wholememory_make_tensor_from_handle(wholememory_tensor_
   return WHOLEMEMORY_SUCCESS;
 }
 
-bool wholememory_tensor_has_handle(wholememory_tensor_t t) { return t->is_wm; }
+/* pointer / bool getters have no error channel: an unknown tensor reads as "no handle" / nullptr */
+bool wholememory_tensor_has_handle(wholememory_tensor_t t) { return wm::obj_known(wm::OBJ_TENSOR, t) && t->is_wm; }
 
 wholememory_handle_t wholememory_tensor_get_memory_handle(wholememory_tensor_t t)
 {
-  return t->is_wm ? t->handle : nullptr;
+  return wm::live(t) && t->is_wm ? t->handle : nullptr;
 }
 
 wholememory_tensor_description_t* wholememory_tensor_get_tensor_description(wholememory_tensor_t t)
 {
-  return &t->desc;
+  return wm::obj_known(wm::OBJ_TENSOR, t) ? &t->desc : nullptr;
 }
 
 wholememory_error_code_t wholememory_tensor_get_global_reference(wholememory_tensor_t t, wholememory_gref_t* gref)
 {
-  if (t == nullptr || gref == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (gref == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (t->is_wm) return wholememory_get_global_reference(gref, t->handle);
   *gref = wholememory_create_continuous_global_reference(t->storage);
   return WHOLEMEMORY_SUCCESS;
@@ -136,7 +142,8 @@ wholememory_error_code_t wholememory_tensor_get_global_reference(wholememory_ten
 
 wholememory_error_code_t wholememory_tensor_map_local_tensor(wholememory_tensor_t t, wholememory_tensor_t* local)
 {
-  if (t == nullptr || local == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (local == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (!t->is_wm) return WHOLEMEMORY_INVALID_VALUE;
   const auto& d = t->desc;
   /* the view may drop trailing rows/columns but must start at row 0 (reference :238-245) */
@@ -159,6 +166,7 @@ wholememory_error_code_t wholememory_tensor_map_local_tensor(wholememory_tensor_
 void* wholememory_tensor_get_data_pointer(wholememory_tensor_t t)
 {
   char* base = nullptr;
+  if (!wm::live(t)) return nullptr;
   if (t->is_wm) {
     if (wholememory_get_memory_type(t->handle) != WHOLEMEMORY_MT_CONTINUOUS) return nullptr;
     if (wholememory_get_global_pointer(reinterpret_cast<void**>(&base), t->handle) != WHOLEMEMORY_SUCCESS) return nullptr;
@@ -170,7 +178,8 @@ void* wholememory_tensor_get_data_pointer(wholememory_tensor_t t)
 
 wholememory_error_code_t wholememory_tensor_get_entry_offsets(size_t* entry_offsets, wholememory_tensor_t t)
 {
-  if (entry_offsets == nullptr || t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (entry_offsets == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (!t->is_wm) {
     entry_offsets[0] = 0;
     entry_offsets[1] = (size_t)t->root->desc.sizes[0];
@@ -187,7 +196,8 @@ wholememory_error_code_t wholememory_tensor_get_entry_offsets(size_t* entry_offs
 
 wholememory_error_code_t wholememory_tensor_get_entry_partition_sizes(size_t* entry_partition, wholememory_tensor_t t)
 {
-  if (entry_partition == nullptr || t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (entry_partition == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (!t->is_wm) {
     entry_partition[0] = (size_t)t->root->desc.sizes[0];
     return WHOLEMEMORY_SUCCESS;
@@ -203,7 +213,8 @@ wholememory_error_code_t wholememory_tensor_get_entry_partition_sizes(size_t* en
 
 wholememory_error_code_t wholememory_tensor_get_local_entry_count(size_t* local_entry_count, wholememory_tensor_t t)
 {
-  if (local_entry_count == nullptr || t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (local_entry_count == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (!t->is_wm) {
     *local_entry_count = (size_t)t->root->desc.sizes[0];
     return WHOLEMEMORY_SUCCESS;
@@ -218,7 +229,8 @@ wholememory_error_code_t wholememory_tensor_get_local_entry_count(size_t* local_
 
 wholememory_error_code_t wholememory_tensor_get_local_entry_start(size_t* local_entry_start, wholememory_tensor_t t)
 {
-  if (local_entry_start == nullptr || t == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (local_entry_start == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   if (!t->is_wm) {
     *local_entry_start = 0;
     return WHOLEMEMORY_SUCCESS;
@@ -236,7 +248,8 @@ wholememory_error_code_t wholememory_tensor_get_subtensor(wholememory_tensor_t t
                                                           int64_t* ends,
                                                           wholememory_tensor_t* sub)
 {
-  if (t == nullptr || starts == nullptr || ends == nullptr || sub == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  if (starts == nullptr || ends == nullptr || sub == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(t);
   const auto& d = t->desc;
   if (d.dim > 2) return WHOLEMEMORY_NOT_IMPLEMENTED;
   wholememory_tensor_description_t nd = d;
@@ -258,6 +271,6 @@ wholememory_error_code_t wholememory_tensor_get_subtensor(wholememory_tensor_t t
   return WHOLEMEMORY_SUCCESS;
 }
 
-wholememory_tensor_t wholememory_tensor_get_root(wholememory_tensor_t t) { return t->root; }
+wholememory_tensor_t wholememory_tensor_get_root(wholememory_tensor_t t) { return wm::live(t) ? t->root : nullptr; }
 
 } /* extern "C" */

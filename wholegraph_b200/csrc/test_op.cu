@@ -43,6 +43,8 @@ extern "C" wholememory_error_code_t wholememory_env_test_op(wholememory_tensor_t
 {
   return wm::guarded("wholememory_env_test_op", [&]() -> wholememory_error_code_t {
     using namespace wm;
+    WM_REQUIRE_LIVE(input_tensor);
+    WM_REQUIRE_LIVE(output_fixed_tensor);
     require_cuda("wholememory_env_test_op");
     auto* id = wholememory_tensor_get_tensor_description(input_tensor);
     auto* od = wholememory_tensor_get_tensor_description(output_fixed_tensor);

@@ -321,9 +321,8 @@ wholememory_error_code_t wholegraph_csr_weighted_sample_without_replacement(whol
 {
   return wm::guarded("wholegraph_csr_weighted_sample_without_replacement", [&]() -> wholememory_error_code_t {
     using namespace wm;
-    if (!wm_csr_row_ptr_tensor || !wm_csr_col_ptr_tensor || !wm_csr_weight_ptr_tensor || !center_nodes_tensor ||
-        !output_sample_offset_tensor)
-      return WHOLEMEMORY_INVALID_INPUT;
+    for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor, center_nodes_tensor, output_sample_offset_tensor})
+      WM_REQUIRE_LIVE(t);
     /* argument checks in the reference's order and with its codes (weighted_sample_without_replacement.cpp:74-126) ... */
     for (auto t : {wm_csr_row_ptr_tensor, wm_csr_col_ptr_tensor, wm_csr_weight_ptr_tensor})
       if (!is_1d(t)) {
@@ -399,7 +398,7 @@ wholememory_error_code_t wholegraph_csr_weighted_sample_without_replacement(whol
 /* host replay of the key stream for weight 1 (reference raft_random_gen.cu:73-108): output[i] = log2(u_i), u in (0,1) */
 wholememory_error_code_t generate_exponential_distribution_negative_float_cpu(int64_t random_seed, int64_t subsequence, wholememory_tensor_t output)
 {
-  if (output == nullptr) return WHOLEMEMORY_INVALID_INPUT;
+  WM_REQUIRE_LIVE(output);
   auto d = *wholememory_tensor_get_tensor_description(output);
   if (d.dim != 1) {
     WM_ERROR("output should be 1D tensor.");

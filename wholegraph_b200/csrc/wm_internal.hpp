@@ -218,6 +218,32 @@ struct wholememory_tensor_ {
 
 namespace wm {
 
+/* ------------------------------------------------------------------ live-object registry (registry.cpp) */
+enum obj_kind { OBJ_COMM, OBJ_HANDLE, OBJ_TENSOR, OBJ_EMBEDDING, OBJ_OPTIMIZER, OBJ_CACHE_POLICY, OBJ_KINDS };
+void obj_register(obj_kind k, const void* p);
+void obj_unregister(obj_kind k, const void* p);
+bool obj_known(obj_kind k, const void* p);   /* false for nullptr */
+std::string api_name(const char* pretty_function); /* "ret f(args)::<lambda()>" -> "f" */
+bool live(wholememory_comm_t c);
+bool live(wholememory_handle_t h);           /* handle and its communicator both alive */
+bool live(wholememory_tensor_t t);           /* tensor alive and, when WholeMemory-backed, its handle too */
+
+/* guard at the top of an extern "C" entry: a null, destroyed or never-issued handle is INVALID_INPUT, never UB */
+#define WM_REQUIRE_LIVE(obj)                                                                        \
+  do {                                                                                              \
+    if (!::wm::live(obj)) {                                                                         \
+      WM_ERROR("%s: `%s` is null, was destroyed, or was never issued by this library", ::wm::api_name(__PRETTY_FUNCTION__).c_str(), #obj); \
+      return WHOLEMEMORY_INVALID_INPUT;                                                             \
+    }                                                                                               \
+  } while (0)
+#define WM_REQUIRE_KNOWN(kind, obj)                                                                 \
+  do {                                                                                              \
+    if (!::wm::obj_known((kind), (obj))) {                                                          \
+      WM_ERROR("%s: `%s` is null, was destroyed, or was never issued by this library", ::wm::api_name(__PRETTY_FUNCTION__).c_str(), #obj); \
+      return WHOLEMEMORY_INVALID_INPUT;                                                             \
+    }                                                                                               \
+  } while (0)
+
 /* ------------------------------------------------------------------ runtime helpers */
 wholememory_error_code_t create_handle(wholememory_handle_t* out,
                                        size_t total_size,
