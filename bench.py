@@ -10,14 +10,18 @@ A "step" is ONE wholememory_gather call over one batch of 1,048,576 uniform-rand
 N=1 workload = BASELINE.json configs[1]: CONTINUOUS/DEVICE table 100M x 256 fp32 (102.4 GB) on one B200.
 N>1 (weak scaling): CHUNKED/DEVICE table of N x 100M rows x 256 fp32 row-sharded over the N GPUs of the box
 and mapped into every GPU (VMM over NVSwitch); every rank gathers 1M rows drawn uniformly from the WHOLE table.
+After the headline, the same measurement runs on the other BASELINE shapes at their per-GPU size (device-timed only):
+  ns = north star, 125M rows/GPU x 256 fp16 (1B x 256 fp16 at N=8);  c3 = configs[2], 125M rows/GPU x 128 fp16.
+Their results are listed under config.other_shapes (and top-level "shapes"); --shapes c2 runs the headline alone.
 
 value       = n * row_out_bytes * N / t   (GB/s of gathered output -- the reference bench's "Bandwidth",
               cpp/bench/wholememory_ops/gather_scatter_bench.cu:363-366), t = max over ranks of the CUDA-event
               time of the K timed calls / K, inputs resident in HBM.
 e2e         = same metric with the step's indices starting in pinned HOST memory (H2D inside the timed region)
               and the gathered rows copied back to pinned host memory (D2H inside the timed region).
-roofline    = algorithmic bytes n*(row_in + row_out + idx) / kernel time against the measured HBM copy
-              bandwidth (N=1) -- for N>1 also the NVLink-ingress bound is reported.
+roofline    = N=1: algorithmic bytes n*(row_in + row_out + idx) / kernel time against the measured HBM copy bandwidth.
+              N>1: the bound is NVLink ingress -- remote bytes n*row*(N-1)/N per GPU / kernel time against the measured
+              peer-copy bandwidth (770 GB/s per direction, B200_PROFILING.md; 900 nominal also given).
 cpu_baseline= the oracle's multithreaded host gather (oracle/wm_oracle.c: oracle_gather_mt) on a bounded sample.
 """
 import argparse
@@ -43,7 +47,8 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
+    p.add_argument("--shapes", default="c2,ns,c3", help="comma list of c2 (headline), ns, c3; the first one is the headline line")
+    p.add_argument("--rows-per-gpu", type=int, default=None, help="custom single shape (diagnostics): overrides --shapes")
     p.add_argument("--dim", type=int, default=DIM)
     p.add_argument("--batch", type=int, default=BATCH)
     p.add_argument("--dtype", default="fp32", choices=["fp32", "fp16"])
@@ -150,41 +155,68 @@ def cpu_baseline(dim, esize, np_dtype, budget_s=12.0):
                       % (passes, n, dim * esize, rows, "pinned (cudaHostAlloc)" if pinned else "pageable", cores)}
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        # the reference library is loaded THROUGH THE SAME BINDING (identical C ABI): oracle/_ref build
-        ref = os.path.join(ROOT, "oracle", "_ref", "libwholegraph_ref.so")
-        if os.path.exists(ref):
-            os.environ["WHOLEGRAPH_B200_LIB"] = ref
-        else:
-            return reference_cpu_arm(args, rank, world)
+SHAPES = {
+    # BASELINE.json configs[1] (weak-scaled for N > 1): the headline
+    "c2": {"rows_per_gpu": 100_000_000, "dim": 256, "dtype": "fp32", "name": "C2: 100M rows/GPU x 256 fp32 (1 KiB rows)"},
+    # north_star: 1B x 256 fp16 over 8 GPUs = 125M rows per GPU
+    "ns": {"rows_per_gpu": 125_000_000, "dim": 256, "dtype": "fp16", "name": "north star: 125M rows/GPU x 256 fp16 (512 B rows; 1B rows at N=8)"},
+    # BASELINE.json configs[2]: 1B x 128 fp16 over 8 GPUs
+    "c3": {"rows_per_gpu": 125_000_000, "dim": 128, "dtype": "fp16", "name": "C3: 125M rows/GPU x 128 fp16 (256 B rows; 1B rows at N=8)"},
+}
+NVLINK_MEASURED_GBS = 770.0  # peer copy per direction measured on this pool (B200_PROFILING.md); nominal 900
 
-    import numpy as np
+
+def traffic_from_profile(shape_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of THIS bench command
+    on the bench-sized table (profiles/r2_gather_<shape>_full_summary.txt, written by tools/ncu_summary.py)."""
+    path = os.path.join(ROOT, "profiles", "r2_gather_%s_full_summary.txt" % shape_key)
+    if not os.path.exists(path):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    got = {}
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[0] not in got and f[2] in unit:
+            got[f[0]] = float(f[1].replace(",", "")) * unit[f[2]]
+    if len(got) != 2:
+        return None, None
+    return got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"], \
+        "profiles/r2_gather_%s_full_summary.txt (ncu --set full of this command: %.3f GB read + %.3f GB written per launch)" % (
+            shape_key, got["dram__bytes_read.sum"] / 1e9, got["dram__bytes_write.sum"] / 1e9)
+
+
+def roofline(world, n, row, ms, impl, shape_key):
+    hbm_peak, peak_src = measured_peaks()
+    alg_bytes = n * (row + row + 8)
+    alg_gbs = alg_bytes / (ms * 1e-3) / 1e9  # per GPU
+    kernel = "wm::row_move_vec_kernel<int64, 32 B units, gather> (wholegraph_b200/csrc/gather_scatter.cuh)" if impl != "reference" else \
+        "reference gather_func_kernel / gather_func_sub_warp_kernel (cpp/src/wholememory_ops/functions/gather_scatter_func.cuh, rebuilt in oracle/_ref)"
+    if world == 1:
+        traffic, traffic_src = traffic_from_profile(shape_key) if impl != "reference" and n == BATCH else (None, None)
+        return {"bound": "hbm", "achieved": round(alg_gbs, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(alg_gbs / hbm_peak, 4),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel, "kernel_ms": round(ms, 4),
+                "algorithmic_bytes_per_launch": alg_bytes}
+    remote_bytes = n * row * (world - 1) / world  # uniform indices over an equally partitioned table
+    ingress = remote_bytes / (ms * 1e-3) / 1e9
+    t_nvl, t_hbm = remote_bytes / (NVLINK_MEASURED_GBS * 1e9), alg_bytes / (hbm_peak * 1e9)
+    return {"bound": "nvlink", "achieved": round(ingress, 2), "peak": NVLINK_MEASURED_GBS, "unit": "GB/s", "frac": round(ingress / NVLINK_MEASURED_GBS, 4),
+            "frac_of_nominal_900": round(ingress / 900.0, 4), "traffic": None, "traffic_source": None,
+            "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md: 770 GB/s; nominal NVLink 5 = 900 GB/s)",
+            "what": "NVLink ingress per GPU = the (N-1)/N of the gathered rows that live on peers / kernel time",
+            "kernel": kernel, "kernel_ms": round(ms, 4), "bound_ms": round(max(t_nvl, t_hbm) * 1e3, 4),
+            "hbm_algorithmic_gbs": round(alg_gbs, 2), "hbm_frac": round(alg_gbs / hbm_peak, 4), "remote_bytes_per_launch": int(remote_bytes),
+            "algorithmic_bytes_per_launch": alg_bytes}
+
+
+def run_shape(ctx, key, shape, args, headline):
+    """Allocate the table of one shape, time K gathers on the device, check the gathered rows, free the table."""
     import torch
     import torch.distributed as dist
-
-    import wholegraph_b200.binding as wmb
-    from wholegraph_b200.torch.wholegraph_env import get_wholegraph_env_fns, wrap_torch_tensor
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
-    uid = wmb.create_unique_id() if rank == 0 else wmb.PyWholeMemoryUniqueID()
-    if world > 1:
-        t = uid.as_tensor().cuda()
-        dist.broadcast(t, 0)
-        uid.as_tensor().copy_(t.cpu())
-    comm = wmb.create_communicator(uid, rank, world)
-
-    th_dtype, wm_dtype, esize = (torch.float32, wmb.DtFloat, 4) if args.dtype == "fp32" else (torch.float16, wmb.DtHalf, 2)
-    dim, n = args.dim, args.batch
-    rows_total = args.rows_per_gpu * world
+    wmb, env, comm, rank, world, local_rank = ctx["wmb"], ctx["env"], ctx["comm"], ctx["rank"], ctx["world"], ctx["local_rank"]
+    from wholegraph_b200.torch.wholegraph_env import wrap_torch_tensor
+    th_dtype, wm_dtype, esize = (torch.float32, wmb.DtFloat, 4) if shape["dtype"] == "fp32" else (torch.float16, wmb.DtHalf, 2)
+    dim, n, rows_per_gpu = shape["dim"], args.batch, shape["rows_per_gpu"]
+    rows_total = rows_per_gpu * world
     mem_type = args.memory_type or ("continuous" if world == 1 else "chunked")
     mt = {"continuous": wmb.MtContinuous, "chunked": wmb.MtChunked, "distributed": wmb.MtDistributed}[mem_type]
     table = wmb.create_wholememory_matrix(wm_dtype, rows_total, dim, -1, comm, mt, wmb.MlDevice)
@@ -196,6 +228,7 @@ def main():
         e = min(local.shape[0], s + chunk)
         ids = torch.arange(first_row + s, first_row + e, device="cuda", dtype=torch.int64)
         local[s:e] = (ids & mask).to(th_dtype).unsqueeze(1)
+    del local
     torch.cuda.synchronize()
     comm.barrier()
 
@@ -204,7 +237,7 @@ def main():
     n_batches = 8  # distinct index batches, cycled: successive steps never re-read the same rows
     idx_dev = [torch.randint(0, rows_total, (n,), device="cuda", dtype=torch.int64, generator=gen) for _ in range(n_batches)]
     if args.index_pattern in ("remote", "local") and world > 1:  # diagnostic: only peer rows / only my rows
-        per = args.rows_per_gpu
+        per = rows_per_gpu
         idx_dev = []
         for _ in range(n_batches):
             r = torch.randint(0, per * (world - 1) if args.index_pattern == "remote" else per, (n,), device="cuda", dtype=torch.int64, generator=gen)
@@ -213,10 +246,9 @@ def main():
             else:
                 r = r + rank * per
             idx_dev.append(r)
-    if args.index_pattern == "sequential":  # diagnostic only: contiguous rows = the kernel's ceiling without DRAM page misses
+    if args.index_pattern == "sequential":  # diagnostic only: contiguous rows
         idx_dev = [(torch.arange(n, device="cuda", dtype=torch.int64) + (b * n * 7) % max(1, rows_total - n)) for b in range(n_batches)]
     out = torch.empty(n, dim, device="cuda", dtype=th_dtype)
-    env = get_wholegraph_env_fns()
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     w_idx = [wrap_torch_tensor(t) for t in idx_dev]
@@ -231,14 +263,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(i)
     # correctness of the timed configuration (cheap, outside the timed region)
     torch.cuda.synchronize()
-    last = (max(args.warmup, 3) - 1) % n_batches
-    assert torch.equal(out[:, 0], (idx_dev[last] & mask).to(th_dtype)) and torch.equal(out[:, dim - 1], out[:, 0]), "gather wrong"
+    last = (warm - 1) % n_batches
+    assert torch.equal(out[:, 0], (idx_dev[last] & mask).to(th_dtype)) and torch.equal(out[:, dim - 1], out[:, 0]), "gather wrong (%s)" % key
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and headline) else None
     if sampler:
         sampler.start()
     sync_all()
@@ -252,14 +285,16 @@ def main():
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # the reference bench's own clock: wall time over K calls + one sync
     sync_all()
     ms = ev0.elapsed_time(ev1) / args.steps
-    # keep the GPU busy a little longer so the clock sampler sees the loaded state even for tiny K
-    t_end = time.time() + 1.0
-    k = 0
-    while time.time() < t_end:
-        step(k)
-        k += 1
-    torch.cuda.synchronize()
-    clocks = sampler.summary() if sampler else None
+    clocks = None
+    if sampler:
+        # keep the GPU busy a little longer so the clock sampler sees the loaded state even for tiny K
+        t_end = time.time() + 1.0
+        k = 0
+        while time.time() < t_end:
+            step(k)
+            k += 1
+        torch.cuda.synchronize()
+        clocks = sampler.summary()
 
     if args.per_step_events and rank == 0:
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -269,15 +304,15 @@ def main():
             b.record(stream)
         torch.cuda.synchronize()
         per = sorted(a.elapsed_time(b) for a, b in evs)
-        print("per-step kernel ms: min %.4f median %.4f max %.4f (loop mean %.4f)" % (per[0], per[len(per) // 2], per[-1], ms), file=sys.stderr)
+        print("%s per-step kernel ms: min %.4f median %.4f max %.4f (loop mean %.4f)" % (key, per[0], per[len(per) // 2], per[-1], ms), file=sys.stderr)
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
 
-    # ---- end to end: indices from pinned host, rows back to pinned host, both copies inside the timed region
+    # ---- end to end (headline only): indices from pinned host, rows back to pinned host, both copies inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if headline and not args.no_e2e:
         idx_host = [t.cpu().pin_memory() for t in idx_dev[:2]]
         out_host = torch.empty(n, dim, dtype=th_dtype).pin_memory()
         idx_stage = torch.empty(n, device="cuda", dtype=torch.int64)
@@ -334,56 +369,101 @@ def main():
         except Exception as ex:  # never let the informational leg break the bench line
             if world == 1:
                 print("device-resident e2e leg skipped: %r" % (ex,), file=sys.stderr)
+        del out_host, idx_host
+
+    row = dim * esize
+    rec = {"key": key, "name": shape["name"], "rows_per_gpu": rows_per_gpu, "rows_total": rows_total, "dim": dim, "dtype": shape["dtype"], "row_bytes": row,
+           "memory_type": mem_type, "ms_per_step": round(ms_max, 4), "value": round(n * row * world / (ms_max * 1e-3) / 1e9, 3), "unit": "GB/s",
+           "per_gpu_gbs_out": round(n * row / (ms_max * 1e-3) / 1e9, 3), "host_ms": host_ms, "clocks": clocks, "e2e": e2e,
+           "roofline": roofline(world, n, row, ms_max, args.impl, key), "checked": "every gathered row equals the closed-form pattern of its index"}
+    del w_idx, w_out, out, idx_dev
+    comm.barrier()
+    wmb.destroy_wholememory_tensor(table)
+    torch.cuda.empty_cache()
+    return rec
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        # the reference library is loaded THROUGH THE SAME BINDING (identical C ABI): oracle/_ref build
+        ref = os.path.join(ROOT, "oracle", "_ref", "libwholegraph_ref.so")
+        if os.path.exists(ref):
+            from oracle.ref_lib_loader import use_library
+            use_library(ref)
+        else:
+            return reference_cpu_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import wholegraph_b200.binding as wmb
+    from wholegraph_b200.torch.wholegraph_env import get_wholegraph_env_fns
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
+    uid = wmb.create_unique_id() if rank == 0 else wmb.PyWholeMemoryUniqueID()
+    if world > 1:
+        t = uid.as_tensor().cuda()
+        dist.broadcast(t, 0)
+        uid.as_tensor().copy_(t.cpu())
+    comm = wmb.create_communicator(uid, rank, world)
+    ctx = {"wmb": wmb, "env": get_wholegraph_env_fns(), "comm": comm, "rank": rank, "world": world, "local_rank": local_rank}
+
+    if args.rows_per_gpu is not None:  # diagnostics: one custom shape
+        plan = [("custom", {"rows_per_gpu": args.rows_per_gpu, "dim": args.dim, "dtype": args.dtype,
+                            "name": "custom: %d rows/GPU x %d %s" % (args.rows_per_gpu, args.dim, args.dtype)})]
+    else:
+        plan = [(k, SHAPES[k]) for k in args.shapes.split(",") if k]
+    recs = []
+    for i, (key, shape) in enumerate(plan):
+        recs.append(run_shape(ctx, key, shape, args, headline=(i == 0)))
+    head, n = recs[0], args.batch
 
     if rank == 0:
-        hbm_peak, peak_src = measured_peaks()
-        row = dim * esize
-        out_gbs = n * row * world / (ms_max * 1e-3) / 1e9
-        alg_bytes = n * (row + row + 8)
-        achieved = alg_bytes / (ms_max * 1e-3) / 1e9  # per GPU
-        t_hbm = alg_bytes / (hbm_peak * 1e9)
-        t_nvl = n * row * (world - 1) / world / 770e9  # measured peer-copy bandwidth per direction (B200_PROFILING.md)
-        bound_ms = max(t_hbm, t_nvl) * 1e3
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed `ncu --set full` capture
-        # (profiles/r1_gather_c2_full_summary.txt: same command, same kernel configuration); not re-measured in this run.
-        traffic, traffic_src = None, None
-        if args.impl != "reference" and world == 1 and (dim, esize, n) == (256, 4, 1 << 20):
-            traffic, traffic_src = 2.100e9, "profiles/r1_gather_c2_full_summary.txt (ncu --set full, 1.081 GB read + 1.020 GB written)"
-        roof = {"bound": "hbm" if t_hbm >= t_nvl else "nvlink", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": "wm::row_move_vec_kernel<int64,16B,gather>", "kernel_ms": round(ms_max, 4),
-                "bound_ms": round(bound_ms, 4), "frac_of_bound_time": round(bound_ms / ms_max, 4),
-                "algorithmic_bytes_per_launch": alg_bytes}
+        row = head["row_bytes"]
+        others = [{k: r[k] for k in ("key", "name", "rows_total", "dim", "dtype", "row_bytes", "memory_type", "value", "unit", "per_gpu_gbs_out",
+                                     "ms_per_step", "roofline", "checked")} for r in recs[1:]]
         line = {
-            "metric": METRIC, "value": round(out_gbs, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if esize == 4 else "f16", "data": "synthetic",
+            "metric": METRIC, "value": head["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if head["dtype"] == "fp32" else "f16", "data": "synthetic",
             "config": {"workload": "%s/DEVICE gather, %d x %d %s table (%.1f GB per GPU), %d uniform-random int64 indices per rank per step"
-                                   % (mem_type.upper(), rows_total, dim, args.dtype, args.rows_per_gpu * row / 1e9, n),
-                       "l2": "inputs larger than L2: table %.0f GB, 8 distinct index batches cycled, 1 GB output per step" % (rows_total * row / 1e9),
-                       "rows_per_gpu": args.rows_per_gpu, "embedding_dim": dim, "indices_per_rank": n, "memory_type": mem_type},
-            "roofline": roof, "gpu_launches": args.steps, "clocks": clocks,
-            "host_timed": {"value": round(n * row * world / (host_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(host_ms, 4),
+                                   % (head["memory_type"].upper(), head["rows_total"], head["dim"], head["dtype"], head["rows_per_gpu"] * row / 1e9, n),
+                       "l2": "inputs larger than L2: table %.0f GB, 8 distinct index batches cycled, %.2f GB output per step" % (head["rows_total"] * row / 1e9, n * row / 1e9),
+                       "rows_per_gpu": head["rows_per_gpu"], "embedding_dim": head["dim"], "indices_per_rank": n, "memory_type": head["memory_type"],
+                       "other_shapes": others},
+            "roofline": head["roofline"], "gpu_launches": args.steps, "clocks": head["clocks"],
+            "host_timed": {"value": round(n * row * world / (head["host_ms"] * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(head["host_ms"], 4),
                            "how": "rank 0 wall clock over the K back-to-back calls + one device synchronize: the reference bench's "
                                   "definition (cpp/bench/wholememory_ops/gather_scatter_bench.cu:363-366); informational"},
+            "shapes": [{"key": r["key"], "value": r["value"], "ms_per_step": r["ms_per_step"], "frac": r["roofline"]["frac"],
+                        "bound": r["roofline"]["bound"]} for r in recs],
         }
-        if e2e:
-            line["e2e"] = e2e
+        if head["e2e"]:
+            line["e2e"] = head["e2e"]
         if args.impl == "reference":
             line["impl"] = "reference"
-            line["cpu_baseline"] = {"value": round(out_gbs, 3), "unit": "GB/s", "cores": 1, "kind": "reference",
+            line["cpu_baseline"] = {"value": head["value"], "unit": "GB/s", "cores": 1, "kind": "reference",
                                     "sample": "reference gather kernels (cpp/src/wholememory_ops) rebuilt for sm_100 from /root/reference "
                                               "into oracle/_ref, same config, same harness; the reference path runs on the GPU, one host thread drives it"}
-            line["e2e"] = line.get("e2e") or {"value": round(out_gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            line["e2e"] = line.get("e2e") or {"value": head["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         elif not args.no_cpu_baseline and world == 1:
+            esize = 4 if head["dtype"] == "fp32" else 2
             try:
-                line["cpu_baseline"] = cpu_baseline(dim, esize, np.float32 if esize == 4 else np.float16)
+                line["cpu_baseline"] = cpu_baseline(head["dim"], esize, np.float32 if esize == 4 else np.float16)
             except Exception as ex:  # the GPU measurement above must not be lost to a host-side problem
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count() or 1, "kind": "port",
                                         "sample": "unavailable: %r" % (ex,)}
         print(json.dumps(line), flush=True)
 
-    wmb.destroy_wholememory_tensor(table)
     wmb.destroy_communicator(comm)
     if world > 1:
         dist.destroy_process_group()

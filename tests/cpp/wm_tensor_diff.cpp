@@ -129,6 +129,21 @@ int main(int argc, char** argv)
     h.local_ptr   = h.part_sizes[me] ? h.rank_base[me] : nullptr;
     h.flat_base   = h.type == WHOLEMEMORY_MT_CONTINUOUS ? arena : nullptr;
     h.peer_mapped = true;
+    /* hand-made objects: tell the library's live-object registry about them (every entry point checks it), and take
+     * them out again when this iteration's scope ends */
+    struct registered {
+      const void *c, *h;
+      registered(const void* c_, const void* h_) : c(c_), h(h_)
+      {
+        wm::obj_register(wm::OBJ_COMM, c);
+        wm::obj_register(wm::OBJ_HANDLE, h);
+      }
+      ~registered()
+      {
+        wm::obj_unregister(wm::OBJ_HANDLE, h);
+        wm::obj_unregister(wm::OBJ_COMM, c);
+      }
+    } reg(&comm, &h);
 
     wholememory_tensor_description_t d;
     wholememory_initialize_tensor_desc(&d);

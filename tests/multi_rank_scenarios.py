@@ -442,6 +442,8 @@ def scenario_gather_scatter_functors(rank, world, comm):
         for ml in (wmb.MlHost, wmb.MlDevice):
             if not comm.wmb_comm.support_type_location(mt, ml):
                 continue
+            if mt == wmb.MtDistributed and ml == wmb.MlHost and world > 1 and os.environ.get("WG_TEST_SHARED_GPU") == "1":
+                continue  # private host shards travel over NCCL, which needs one GPU per rank (covered by test_one_rank_per_gpu)
             table = wmb.create_wholememory_matrix(wmb.DtFloat, count, dim, -1, comm.wmb_comm, mt, ml, partition)
             mine = torch.arange(rank, count, world, dtype=torch.int64)
             wm_ops.wholememory_scatter_functor(closed_form(mine).cuda(), mine.cuda(), table)

@@ -92,7 +92,13 @@ def main():
         urows, ug = O.dedup_gradients(idx, g)
         O.optimizer_step("adam", w, urows, ug, 0.02, state=(m, v), b12=b12, beta1=0.85, weight_decay=0.01)
     torch.cuda.synchronize()
-    assert np.allclose(local.cpu().numpy(), w, rtol=1e-5, atol=1e-5), "LazyAdam through the reference binding differs from the oracle"
+    got = local.cpu().numpy()
+    if not np.allclose(got, w, rtol=1e-5, atol=1e-5):
+        bad = np.argwhere(~np.isclose(got, w, rtol=1e-5, atol=1e-5))
+        cnt = np.bincount(idx, minlength=rows)
+        lines = ["row %d col %d: got %r oracle %r (dups of this row in the last step: %d)" % (r, c, got[r, c], w[r, c], cnt[r]) for r, c in bad[:8]]
+        raise AssertionError("LazyAdam through the reference binding differs from the oracle: %d of %d elements in %d rows, max abs err %g\n%s"
+                             % (bad.shape[0], got.size, np.unique(bad[:, 0]).size, np.abs(got - w).max(), "\n".join(lines)))
     # embedding gather through the reference binding
     gi = rng.integers(0, rows, size=777).astype(np.int64)
     out = torch.empty(777, dim, device="cuda")

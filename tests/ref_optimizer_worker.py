@@ -19,6 +19,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from oracle.ref_lib_loader import apply_env  # noqa: E402  (WHOLEGRAPH_B200_LIB: run this harness on the reference's library)
+
+apply_env()
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SMALL = os.environ.get("WG_GOLDEN_SMALL") == "1"  # compact sizes for the committed golden vectors (tools/make_golden.sh)
@@ -87,6 +90,17 @@ def run_api(ci, with_states=True):
     return res
 
 
+_INITED = False
+
+
+def _init_once(wmb):
+    """The reference's wholememory_init refuses a second call (initialize.cpp:40); this repo's is idempotent."""
+    global _INITED
+    if not _INITED:
+        wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
+        _INITED = True
+
+
 def run_reference(ci):
     import torch
     import wholegraph_b200.binding as wmb
@@ -100,7 +114,7 @@ def run_reference(ci):
     fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [ctypes.c_int] + \
                   [ctypes.c_float] * 2 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
     torch.cuda.set_device(0)
-    wmb.init(0, wmb.WholeMemoryLogLevel.LevWarn)
+    _init_once(wmb)
     w0, steps = case_inputs(ci)
     stride = (dim + 3) // 4 * 4  # align_embedding_dim for fp32: 16-byte rows (reference embedding.cpp:43-50)
     w = torch.zeros(ROWS, stride, device="cuda")

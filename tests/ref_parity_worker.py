@@ -8,6 +8,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from oracle.ref_lib_loader import apply_env  # noqa: E402  (WHOLEGRAPH_B200_LIB: run this harness on the reference's library)
+
+apply_env()
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # (mem_type, location, table dtype, dense dtype, cols, stride, index dtype, n)

@@ -104,7 +104,7 @@ def test_every_entry_family_refuses_handles_after_finalize():
     h = t.get_wholememory_handle()
     sub = t.get_sub_tensor((0, 0), (32, 8))
     opt = wmb.create_optimizer(wmb.OptSgd, {})
-    assert comm.get_rank() == 0 and h.get_local_size() == 64 * 8 * 4
+    assert comm.get_rank() == 0 and h.get_local_memory()[1] == 64 * 8 * 4
     c_comm, c_h, c_t = comm.comm_id, h.wholememory_handle, t.wholememory_tensor
 
     wmb.finalize()   # destroys the communicator, which takes the handle's memory with it
@@ -116,8 +116,7 @@ def test_every_entry_family_refuses_handles_after_finalize():
     refused(wmb.create_wholememory_matrix, wmb.DtFloat, 64, 8, -1, comm, wmb.MtChunked, wmb.MlHost)
     refused(wmb.create_embedding, desc(64, 8), comm, wmb.MtChunked, wmb.MlHost, wmb.create_non_cache_policy())   # the round-1 crash
     # handle family
-    refused(h.get_local_size); refused(h.get_rank_partition_sizes) if hasattr(h, "get_rank_partition_sizes") else None
-    refused(h.get_global_pointer)
+    refused(h.get_local_memory); refused(h.get_global_pointer); refused(h.get_global_reference); refused(h.get_rank_memory, 0)
     for f in (lib.wholememory_get_total_size, lib.wholememory_get_data_granularity):
         f.restype = ctypes.c_size_t
         assert f(c_h) == 0
@@ -153,7 +152,7 @@ def test_every_entry_family_refuses_handles_after_finalize():
     wmb.init(0, wmb.WholeMemoryLogLevel.LevFatal)
     comm2 = wmb.create_communicator(wmb.create_unique_id(), 0, 1)
     t2 = wmb.create_wholememory_matrix(wmb.DtFloat, 64, 8, -1, comm2, wmb.MtChunked, wmb.MlHost)
-    assert t2.get_wholememory_handle().get_local_size() == 64 * 8 * 4
+    assert t2.get_wholememory_handle().get_local_memory()[1] == 64 * 8 * 4
     wmb.destroy_wholememory_tensor(t2)
     wmb.destroy_communicator(comm2)
     print("ALL-OK")
@@ -165,7 +164,7 @@ def test_embedding_handles_after_finalize():
     _run(PRELUDE + """
     comm = wmb.create_communicator(wmb.create_unique_id(), 0, 1)
     emb = wmb.create_embedding(desc(64, 8), comm, wmb.MtChunked, wmb.MlHost, wmb.create_non_cache_policy())
-    c_e = emb.wm_embedding if hasattr(emb, "wm_embedding") else emb.get_c_handle()
+    c_e = emb.wm_embedding
     lib.wholememory_embedding_get_embedding_tensor.restype = ctypes.c_void_p
     assert lib.wholememory_embedding_get_embedding_tensor(c_e) is not None
     wmb.finalize()

@@ -14,6 +14,9 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from oracle.ref_lib_loader import apply_env  # noqa: E402  (WHOLEGRAPH_B200_LIB: run this harness on the reference's library)
+
+apply_env()
 import wholegraph_b200.binding as wmb  # noqa: E402
 import wholegraph_b200.torch as wgth  # noqa: E402
 from wholegraph_b200.torch.wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor  # noqa: E402

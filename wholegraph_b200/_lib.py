@@ -14,9 +14,10 @@ from ctypes import (POINTER, Structure, c_bool, c_char, c_char_p, c_float, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libwholegraph.so")
-# Test/bench hook ONLY: load another build of the SAME C ABI (the reference's own library rebuilt under
-# oracle/_ref) through this binding, to time and compare it.  Missing symbols are tolerated in that mode.
-_ALT = os.environ.get("WHOLEGRAPH_B200_LIB")
+# No environment switch here.  The parity tests and the bench run this same binding on the reference's own library by
+# executing this file with the path pre-seeded (oracle/ref_lib_loader.py, outside the package); symbols that library
+# lacks are tolerated in that mode only.
+_ALT = globals().get("_LIB_PATH_PRESET")
 if _ALT:
     LIB_PATH = _ALT
 

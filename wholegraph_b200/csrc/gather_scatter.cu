@@ -4,7 +4,9 @@
  * (cpp/src/wholememory_ops/functions/gather_scatter_func.cuh:378-517, :600-661) and its
  * dtype-pair registry (register.hpp): same accepted dtype pairs plus bf16.
  */
-#include "gather_bulk.cuh"
+#ifdef WG_DEV_KNOBS
+#include "gather_bulk.cuh" /* copy-engine variant: measured slower everywhere on B200, kept for sweeps */
+#endif
 #include "gather_scatter.cuh"
 #include "ops_internal.hpp"
 
@@ -14,8 +16,18 @@ namespace wm {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll  = 4;
+/* Launch shape, measured on B200 with tools/rowmove_lab.cu (profiles/README.md, round 2; 1,048,576 rows per launch):
+ *   - 128-thread CTAs, ONE batch per warp, non-persistent grid (the hardware CTA scheduler walks the index array in
+ *     order); a warp batch of ~4 KiB (R = 4096 / row_bytes rows): 256 B rows 0.919 -> 0.960 of HBM, 512 B 0.934 -> 0.987,
+ *     1 KiB 0.979 -> 0.998.  Smaller batches (2 KiB) lose 3-9 %, a persistent grid-stride loop 5-9 %.
+ *   - 256-bit accesses (LDG.E.256 / STG.E.256) wherever every address, stride and the row size are multiples of 32 B:
+ *     +2-4 % (1 KiB rows: 1.017 of the measured copy bandwidth).
+ *   - programmatic dependent launch: back-to-back calls overlap their launch ramp with the predecessor's tail, +1.5-2.5 %
+ *     on the short kernels (256 B rows: 0.952 -> 0.976).
+ * The copy-engine (cp.async.bulk) kernel measured 0.84-0.89 on the same shapes and is built only with -DWG_DEV_KNOBS. */
+constexpr int kThreads     = 128;
+constexpr int kUnroll      = 4;
+constexpr int kBatchBytes  = 4096;
 
 inline int pow2_divisor(uint64_t v, int cap)
 {
@@ -24,11 +36,17 @@ inline int pow2_divisor(uint64_t v, int cap)
   return a;
 }
 
-/* developer knobs for sweeps on the GPU box (unset in production): WG_UNROLL, WG_BATCH_ROWS, WG_BLOCKS_PER_SM */
+/* Sweep knobs for the GPU box (WG_UNROLL, WG_THREADS, WG_BATCH_ROWS, WG_BLOCKS_PER_SM, WG_CACHE_POLICY, WG_GRID_MODE,
+ * WG_VEC, WG_PDL, WG_BULK*): compiled in only with -DWG_DEV_KNOBS (make DEV_KNOBS=1); the shipped library ignores them. */
 int env_int(const char* name, int dflt)
 {
+#ifdef WG_DEV_KNOBS
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
 }
 int tuned_unroll()
 {
@@ -42,19 +60,46 @@ int tuned_threads()
   return t;
 }
 
+/* One launch path for every instantiation: programmatic stream serialization when allowed (the kernels call
+ * griddepcontrol.wait before their first dependent read), plain launch otherwise or when the attribute is refused. */
+template <typename K, typename... Args>
+void launch_row_kernel(K kernel, int grid, int threads, cudaStream_t s, Args... args)
+{
+  static const int pdl_mode = env_int("WG_PDL", 1);
+  static bool pdl_ok        = pdl_mode != 0;
+  if (pdl_ok) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim  = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.stream   = s;
+    cudaLaunchAttribute attr;
+    attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                       = &attr;
+    cfg.numAttrs                                    = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e == cudaSuccess) return;
+    if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) WM_CUDA(e);
+    (void)cudaGetLastError(); /* this driver / stream does not take the attribute: never try again */
+    pdl_ok = false;
+  }
+  kernel<<<grid, threads, 0, s>>>(args...);
+}
+
 template <typename IdxT, int VEC, bool GATHER>
 void launch_vec(const table_ref& t, const row_geom& g, const void* idx, int64_t n, char* dense, int grid, cudaStream_t s)
 {
   const IdxT* ip = static_cast<const IdxT*>(idx);
+#ifdef WG_DEV_KNOBS
   if constexpr (VEC == 16) {
-    /* the 16-byte path is the hot one: loads-in-flight per lane is tunable */
     switch (tuned_unroll()) {
-      case 2: row_move_vec_kernel<IdxT, VEC, GATHER, 2><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense); return;
-      case 8: row_move_vec_kernel<IdxT, VEC, GATHER, 8><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense); return;
+      case 2: launch_row_kernel(row_move_vec_kernel<IdxT, VEC, GATHER, 2>, grid, tuned_threads(), s, t, g, ip, n, dense); return;
+      case 8: launch_row_kernel(row_move_vec_kernel<IdxT, VEC, GATHER, 8>, grid, tuned_threads(), s, t, g, ip, n, dense); return;
       default: break;
     }
   }
-  row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll><<<grid, tuned_threads(), 0, s>>>(t, g, ip, n, dense);
+#endif
+  launch_row_kernel(row_move_vec_kernel<IdxT, VEC, GATHER, kUnroll>, grid, tuned_threads(), s, t, g, ip, n, dense);
 }
 
 template <typename IdxT, bool GATHER>
@@ -73,16 +118,11 @@ void launch_vec_w(int vec, const table_ref& t, const row_geom& g, const void* id
 int vec_blocks_per_sm()
 {
   static int occ = [] {
-    int o = 0;
-    cudaError_t e;
-    switch (tuned_unroll()) {
-      case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, 2>, kThreads, 0); break;
-      case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, 8>, kThreads, 0); break;
-      default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 16, true, kUnroll>, kThreads, 0); break;
-    }
+    int o         = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, row_move_vec_kernel<int64_t, 32, true, kUnroll>, tuned_threads(), 0);
     if (e != cudaSuccess || o <= 0) {
       (void)cudaGetLastError();
-      o = 4;
+      o = 8;
     }
     o = env_int("WG_BLOCKS_PER_SM", o);
     return o;
@@ -90,8 +130,6 @@ int vec_blocks_per_sm()
   return occ;
 }
 
-/* rows per warp batch + grid size.  Enough batches to balance the persistent grid, small enough
- * batches that one warp does not serialise a long copy. */
 /* magic multiplier for floor(w / d) = (w * magic) >> 40, exact while w < 2^20 and d < 2^20 */
 void set_units(row_geom* g, int64_t units_per_row)
 {
@@ -101,29 +139,30 @@ void set_units(row_geom* g, int64_t units_per_row)
   g->div_magic     = (((uint64_t)1 << 40) + (uint64_t)units_per_row - 1) / (uint64_t)units_per_row;
 }
 
+/* rows per warp batch + grid size */
 void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_rows, int* grid)
 {
   int total_sms = sm_count();
   if (sms <= 0 || sms > total_sms) sms = total_sms;
+  const int wpc       = tuned_threads() / 32;
   int64_t max_grid    = (int64_t)sms * blocks_per_sm;
-  int64_t total_warps = max_grid * (kThreads / 32);
+  int64_t total_warps = max_grid * wpc;
   int R               = 32;
-  while (R > 1 && (int64_t)R * row_bytes > 16384) R >>= 1;
-  while (R > 1 && n / R < total_warps * 4) R >>= 1;
+  while (R > 1 && (int64_t)R * row_bytes > kBatchBytes) R >>= 1;
+  while (R > 1 && n / R < total_warps * 2) R >>= 1; /* small calls: spread the rows over the whole GPU */
   static const int forced_rows = env_int("WG_BATCH_ROWS", 0);
   if (forced_rows > 0) R = forced_rows;
   int64_t nbatch = (n + R - 1) / R;
-  const int wpc  = tuned_threads() / 32;
   int64_t need   = (nbatch + wpc - 1) / wpc;
   *batch_rows    = R;
   *grid          = (int)std::max<int64_t>(1, std::min(max_grid, need));
-  /* Unless the caller restricts the SM budget, launch ONE BATCH PER WARP and let the hardware CTA scheduler walk the
-   * index array in order: measured 0.340 ms vs 0.372 ms for the persistent grid-stride form on C2 (0.966 vs 0.883 of
-   * HBM peak, profiles/README.md).  WG_GRID_MODE=0 restores the persistent grid (developer knob). */
+  /* Unless the caller restricts the SM budget (gather_sms), launch ONE BATCH PER WARP and let the hardware CTA scheduler
+   * walk the index array in order; a budget turns the same kernel into a persistent grid of sms * blocks_per_sm CTAs. */
   static const int grid_mode = env_int("WG_GRID_MODE", 1);
   if (grid_mode == 1 && sms == total_sms) *grid = (int)std::min<int64_t>(need, 0x7fffffff);
 }
 
+#ifdef WG_DEV_KNOBS
 /* TMA-bulk variant (gather_bulk.cuh).  Returns false when the shape does not qualify. */
 template <typename IdxT, bool GATHER>
 bool launch_bulk(const table_ref& t, row_geom g, const void* idx, int64_t n, char* dense, int64_t row_bytes, int sms, cudaStream_t s)
@@ -153,6 +192,7 @@ bool launch_bulk(const table_ref& t, row_geom g, const void* idx, int64_t n, cha
   kernel<<<grid, kBulkWarps * 32, smem, s>>>(t, g, static_cast<const IdxT*>(idx), n, dense, (int)row_bytes);
   return true;
 }
+#endif
 
 }  // namespace
 
@@ -215,20 +255,17 @@ void row_move(bool gather,
 
   if (td.dtype == dd.dtype) {
     const int64_t row_bytes = td.sizes[1] * et;
-    /* widest unit: 16 bytes; WG_VEC32=1 (developer knob, not yet measured) tries sm_100's 256-bit accesses where every
-     * address, stride and the row size are multiples of 32 bytes */
-    static const int max_vec = env_int("WG_VEC32", 0) != 0 ? 32 : 16;
-    int vec                 = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, max_vec);
-    g.row_elems             = (int)td.sizes[1];
+    /* widest unit: 32 bytes (sm_100's 256-bit global accesses) where every address, stride and the row size allow it,
+     * else 16, 8, ... 1 */
+    static const int max_vec = env_int("WG_VEC", 32);
+    int vec                  = pow2_divisor(t_bits | d_bits | (uint64_t)row_bytes, max_vec);
+    g.row_elems              = (int)td.sizes[1];
     set_units(&g, row_bytes / vec);
-    int grid                = 1;
-    /* Kernel choice, measured on B200 (profiles/README.md): the LDG/STG kernel launched one-batch-per-warp wins
-     * everywhere -- local HBM 0.345 ms (bulk: 0.377-0.390), 2 GPUs uniform indices 0.820-0.825 ms (bulk: 0.829-0.845),
-     * remote-only 669 GB/s (bulk: 657-660).  The copy-engine kernel (cp.async.bulk, gather_bulk.cuh) stays available
-     * behind WG_BULK=1; it frees the SMs' LSU/register path and is the basis for a future SM-budgeted (gather_sms) mode. */
+    int grid                 = 1;
+#ifdef WG_DEV_KNOBS
     static const int bulk_mode = env_int("WG_BULK", 0);
-    const bool use_bulk        = bulk_mode != 0;
-    if (use_bulk && vec == 16 && row_bytes >= 64) {
+    if (bulk_mode != 0 && vec >= 16 && row_bytes >= 64) {
+      set_units(&g, row_bytes / 16);
       bool done = gather ? (idx64 ? launch_bulk<int64_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream)
                                   : launch_bulk<int32_t, true>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream))
                          : (idx64 ? launch_bulk<int64_t, false>(tref, g, idx_ptr, n, dense_ptr, row_bytes, sms, stream)
@@ -237,7 +274,9 @@ void row_move(bool gather,
         WM_CUDA(cudaGetLastError());
         return;
       }
+      set_units(&g, row_bytes / vec);
     }
+#endif
     plan(n, row_bytes, sms, vec_blocks_per_sm(), &g.batch_rows, &grid);
     if (gather) {
       if (idx64) launch_vec_w<int64_t, true>(vec, tref, g, idx_ptr, n, dense_ptr, grid, stream);

@@ -145,9 +145,15 @@ class bootstrap {
   void recv_all(int fd, void* p, size_t n);
   void send_fd(int sock, int fd);
   int recv_fd(int sock);
+  void socket_allgather(const void* send, void* recv, size_t bytes);
+  void setup_mailbox();                                              /* collective, over the sockets */
+  void mailbox_allgather(const void* send, void* recv, size_t bytes); /* bytes <= mailbox payload */
+  void check_sockets_alive();
+  struct mailbox;
   int rank_, size_;
   int listen_fd_ = -1;
   std::vector<int> peers_; /* root: socket per rank (index 0 unused); others: peers_[0] = root */
+  mailbox* mbox_ = nullptr; /* shared-memory fast path for small collectives; nullptr = sockets only */
 };
 
 }  // namespace wm
