@@ -198,6 +198,77 @@ def main():
             out.append({"op": "gather fp32 %dx%d, %d rows, gather_sms=%d" % (rows, dim, n, sms), "ms": round(ms, 4),
                         "alg_GBps": round(alg / ms / 1e6, 1), "frac_hbm": round(alg / ms / 1e6 / HBM, 4)})
         wgth.destroy_wholememory_tensor(t)
+    if "c1" in args.what:
+        # a7 / BASELINE config C1: wholememory_gather 1M x 64 fp32, single rank, HOST-location memory, 100,000 int64 ids.
+        # The reference sorts the ids first for host memory (gather_op.cpp:116-120, sort_indices_func.cu:42-92); this library
+        # does not.  Timed on whichever library is loaded, random ids and the same ids pre-sorted by the caller (= what a sort
+        # inside the call could buy at best, without its cost).
+        rows, dim, n = 1_000_000, 64, 100_000
+        t = wgth.create_wholememory_tensor(comm, "continuous", "cpu", [rows, dim], torch.float32, [dim, 1])
+        idx = torch.randint(0, rows, (n,), device="cuda", generator=g)
+        dst = torch.empty(n, dim, device="cuda")
+        w_dst = wrap_torch_tensor(dst)
+        for name, ids in (("random ids", idx), ("caller-sorted ids", torch.sort(idx)[0].contiguous())):
+            w_i = wrap_torch_tensor(ids)
+
+            def f():
+                wmb.wholememory_gather_op(t.wmb_tensor, w_i, w_dst, env, get_stream())
+            ms = timeit(f, steps=30, warmup=5)
+            out.append({"op": "C1 gather HOST/CONTINUOUS %dx%d fp32, %d int64 ids, %s" % (rows, dim, n, name), "ms": round(ms, 4),
+                        "GBps_out": round(n * dim * 4 / ms / 1e6, 2)})
+        wgth.destroy_wholememory_tensor(t)
+    if "overlap" in args.what:
+        # f2: a loader overlaps feature gathering with the next batch's sampling by giving the gather an SM budget
+        # (gather_sms; reference gather_scatter_func.cuh:440,506).  Gather on one stream, unweighted sampling on another:
+        # alone, back to back, and concurrent for several budgets.
+        rows, dim, n = args.rows, 256, 1 << 20
+        t = wgth.create_wholememory_tensor(comm, "continuous", "cuda", [rows, dim], torch.float32, [dim, 1])
+        idxs = [torch.randint(0, rows, (n,), device="cuda", generator=g) for _ in range(4)]
+        dst = torch.empty(n, dim, device="cuda")
+        w_dst, w_idx = wrap_torch_tensor(dst), [wrap_torch_tensor(i) for i in idxs]
+        nodes = 10_000_000
+        deg = torch.clamp((torch.rand(nodes, device="cuda", generator=g) ** -0.7).long(), max=10000)
+        row_ptr = torch.zeros(nodes + 1, dtype=torch.int64, device="cuda")
+        row_ptr[1:] = torch.cumsum(deg, 0)
+        edges = int(row_ptr[-1].item())
+        rp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [nodes + 1], torch.int64, [1])
+        cp = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [edges], torch.int32, [1])
+        rp.get_local_tensor()[0].copy_(row_ptr)
+        cp.get_local_tensor()[0].copy_(torch.randint(0, nodes, (edges,), device="cuda", dtype=torch.int32, generator=g))
+        centers = torch.randint(0, nodes, (262144,), device="cuda", generator=g)
+        s_gather, s_sample = torch.cuda.Stream(), torch.cuda.Stream()
+        reps = 8  # gathers / sampling calls per measurement
+
+        def gathers(sms):
+            with torch.cuda.stream(s_gather):
+                for i in range(reps):
+                    wmb.wholememory_gather_op(t.wmb_tensor, w_idx[i % 4], w_dst, env, get_stream(), sms)
+
+        def samples():
+            with torch.cuda.stream(s_sample):
+                for _ in range(reps):
+                    wgth.unweighted_sample_without_replacement(rp.wmb_tensor, cp.wmb_tensor, centers, 25, random_seed=7)
+
+        def wall(fn):
+            import time
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / 3 * 1e3
+
+        t_g = wall(lambda: gathers(-1))
+        t_s = wall(samples)
+        out.append({"op": "overlap: %d gathers (fp32 %dx%d, %d rows) alone, all SMs" % (reps, rows, dim, n), "ms": round(t_g, 3)})
+        out.append({"op": "overlap: %d sampling calls (262144 centers, k=25) alone" % reps, "ms": round(t_s, 3)})
+        for sms in (-1, 132, 116, 96, 64):
+            t_both = wall(lambda: (gathers(sms), samples()))
+            out.append({"op": "overlap: both, two streams, gather_sms=%d" % sms, "ms": round(t_both, 3), "serial_sum_ms": round(t_g + t_s, 3),
+                        "vs_serial": round((t_g + t_s) / t_both, 3)})
+        for x in (t, rp, cp):
+            wgth.destroy_wholememory_tensor(x)
     for o in out:
         print(json.dumps(o))
 
