@@ -18,6 +18,12 @@ def use_library(path):
         if os.path.abspath(loaded) != os.path.abspath(path):
             raise RuntimeError("wholegraph_b200 is already bound to %s; use_library() must run before the first import" % loaded)
         return
+    # torch first: its bundled NCCL (2.28) must be the libnccl.so.2 of the process -- the reference library links the
+    # system's older one and, loaded RTLD_GLOBAL before torch, would leave libtorch_cuda.so with unresolved symbols
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     src = os.path.join(_ROOT, "wholegraph_b200", "_lib.py")
     spec = importlib.util.spec_from_file_location("wholegraph_b200._lib", src)
     mod = importlib.util.module_from_spec(spec)

@@ -515,7 +515,51 @@ def scenario_weighted_sampling(rank, world, comm):
                 wmb.destroy_wholememory_tensor(t)
 
 
-SCENARIOS = {"gather_scatter_functors": scenario_gather_scatter_functors, "sampling_grid": scenario_sampling_grid, "file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
+def scenario_failing_together(rank, world, comm):
+    """A rank-local failure inside a collective call reaches every rank as an error instead of leaving the others in a
+    rendezvous: (1) one rank names a part file that does not exist, (2) the ranks pass different row partitions with the
+    same total, (3) the communicator still works afterwards."""
+    import tempfile
+    import torch
+    import wholegraph_b200.binding as wmb
+    rows, dim = 4096, 16
+    t = wmb.create_wholememory_matrix(wmb.DtFloat, rows, dim, -1, comm.wmb_comm, wmb.MtChunked, wmb.MlDevice)
+    tmp = os.path.join(tempfile.gettempdir(), "wg_failing_together_%d" % os.getppid())
+    if rank == 0:
+        np.arange(rows * dim, dtype=np.float32).tofile(tmp)
+    comm.barrier()
+    names = [tmp if rank != world - 1 else tmp + ".does-not-exist"]
+    try:
+        t.from_filelist(names)
+        raised = None
+    except Exception as e:  # the rank with the missing file reports INVALID_INPUT, the others learn that it failed
+        raised = e
+    assert raised is not None, "rank %d: load with a missing file on rank %d did not fail here" % (rank, world - 1)
+    t.from_filelist([tmp])  # same call, good arguments: works, so nobody is out of step
+    local, first = t.get_local_tensor(wmb.MlDevice, torch.cuda.current_device())
+    assert torch.equal(local.cpu().reshape(-1), torch.arange(first * dim, (first + local.shape[0]) * dim, dtype=torch.float32))
+    comm.barrier()
+    wmb.destroy_wholememory_tensor(t)
+    if world > 1:
+        part = [rows // world] * world
+        part[-1] += rows - sum(part)
+        if rank == 1:  # same total, different split
+            part[0] -= 1
+            part[-1] += 1
+        try:
+            bad = wmb.create_wholememory_matrix(wmb.DtFloat, rows, dim, -1, comm.wmb_comm, wmb.MtChunked, wmb.MlDevice, part)
+            wmb.destroy_wholememory_tensor(bad)
+            raise AssertionError("ranks with different partitions built a table")
+        except RuntimeError as e:
+            assert "ogic" in str(e), e  # WHOLEMEMORY_LOGIC_ERROR on every rank
+    comm.barrier()
+    t2 = wmb.create_wholememory_matrix(wmb.DtFloat, rows, dim, -1, comm.wmb_comm, wmb.MtContinuous, wmb.MlDevice)
+    wmb.destroy_wholememory_tensor(t2)
+    if rank == 0:
+        os.unlink(tmp)
+
+
+SCENARIOS = {"failing_together": scenario_failing_together, "gather_scatter_functors": scenario_gather_scatter_functors, "sampling_grid": scenario_sampling_grid, "file_io_grid": scenario_file_io_grid, "weighted_sampling": scenario_weighted_sampling, "file_io": scenario_file_io, "gather_scatter": scenario_gather_scatter, "gradient": scenario_gradient, "sampling": scenario_sampling}
 
 
 def worker(rank, world, port, ngpus, scenario, env, results):

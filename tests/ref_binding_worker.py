@@ -87,8 +87,10 @@ def main():
     for _ in range(2):
         idx = (rng.zipf(1.3, size=n) % rows).astype(np.int64)
         g = rng.standard_normal((n, dim)).astype(np.float32)
-        rwmb.EmbeddingGatherGradientApply(emb, wrap(torch.from_numpy(idx).cuda()), wrap(torch.from_numpy(g).cuda()), False, 0.02,
-                                          env.get_env_fns(), stream)
+        # WrappedLocalTensor keeps a POINTER, not the tensor: the operands must stay referenced until the call has been
+        # issued (the first version passed temporaries; torch handed the freed index block to the gradient copy)
+        idx_t, g_t = torch.from_numpy(idx).cuda(), torch.from_numpy(g).cuda()
+        rwmb.EmbeddingGatherGradientApply(emb, wrap(idx_t), wrap(g_t), False, 0.02, env.get_env_fns(), stream)
         urows, ug = O.dedup_gradients(idx, g)
         O.optimizer_step("adam", w, urows, ug, 0.02, state=(m, v), b12=b12, beta1=0.85, weight_decay=0.01)
     torch.cuda.synchronize()
@@ -102,7 +104,8 @@ def main():
     # embedding gather through the reference binding
     gi = rng.integers(0, rows, size=777).astype(np.int64)
     out = torch.empty(777, dim, device="cuda")
-    rwmb.EmbeddingGatherForward(emb, wrap(torch.from_numpy(gi).cuda()), wrap(out), False, env.get_env_fns(), stream)
+    gi_t = torch.from_numpy(gi).cuda()
+    rwmb.EmbeddingGatherForward(emb, wrap(gi_t), wrap(out), False, env.get_env_fns(), stream)
     torch.cuda.synchronize()
     assert torch.equal(out, local[torch.from_numpy(gi).cuda()])
     emb.destroy_embedding()
@@ -120,7 +123,8 @@ def main():
     centers = rng.integers(0, nodes, size=600).astype(np.int64)
     offsets = torch.empty(601, dtype=torch.int32, device="cuda")
     c_dst, c_lid, c_gid = _Ctx(), _Ctx(), _Ctx()
-    rwmb.csr_unweighted_sample_without_replacement(rp, cp, wrap(torch.from_numpy(centers).cuda()), 25, wrap(offsets), id(c_dst), id(c_lid),
+    centers_t = torch.from_numpy(centers).cuda()  # referenced until the call returns (the env callbacks allocate from torch inside it)
+    rwmb.csr_unweighted_sample_without_replacement(rp, cp, wrap(centers_t), 25, wrap(offsets), id(c_dst), id(c_lid),
                                                    id(c_gid), 4321, env.get_env_fns(), stream)
     torch.cuda.synchronize()
     eo, ed, el, eg = O.unweighted_sample(row_ptr, col, centers, 25, 4321)

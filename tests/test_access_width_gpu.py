@@ -34,7 +34,7 @@ def test_gather_and_scatter_at_every_access_width(dt, cols, stride, out_stride, 
     import gpu_utils as G
     esz = np.dtype(O.NP_OF[dt]).itemsize
     assert np.gcd.reduce([cols * esz, stride * esz, out_stride * esz, 32]) == unit  # the case pins the width it says it does
-    rows = 50000
+    rows = 100000
     rng = np.random.default_rng(cols * 7 + n + unit)
     comm = G.single_comm()
     table, view = G.create_table(comm, mem_type, "cuda", dt, rows, cols, stride)
@@ -60,3 +60,33 @@ def test_gather_and_scatter_at_every_access_width(dt, cols, stride, out_stride, 
     got = G.torch_to_np(view, dt)
     G.wmb.destroy_wholememory_tensor(table)
     assert got[:, :cols].tobytes() == host[:, :cols].tobytes(), "scatter"
+
+
+@pytest.mark.parametrize("dt,cols", [(O.DT_INT8, 100001), (O.DT_FLOAT, 300000), (O.DT_HALF, 70001)])
+def test_very_long_rows(dt, cols):
+    """Rows far beyond the batched-row map's range (round 1 refused more than 32,767 units per row): one row per warp,
+    any width -- 100,001-byte int8 rows move in 1-byte units, 1.2 MB fp32 rows in 32-byte units."""
+    import gpu_utils as G
+    rows, n = 37, 50
+    rng = np.random.default_rng(cols)
+    comm = G.single_comm()
+    table, view = G.create_table(comm, "chunked", "cuda", dt, rows, cols, cols)
+    host = G.random_table(rng, dt, rows, cols)
+    view.copy_(G.np_to_torch(host, dt))
+    idx = rng.integers(0, rows, size=n).astype(np.int64)
+    idx[5] = -1
+    sentinel = G.random_table(rng, dt, n, cols)
+    out_t = G.np_to_torch(sentinel.copy(), dt).cuda()
+    G.gather(table, G.idx_to_cuda(idx), out_t)
+    torch.cuda.synchronize()
+    exp = sentinel.copy()
+    O.gather(host, dt, idx, dt, out=exp)
+    assert G.torch_to_np(out_t, dt).tobytes() == exp.tobytes(), "gather"
+    sidx = rng.permutation(rows)[:20].astype(np.int64)
+    src = G.random_table(rng, dt, 20, cols)
+    G.scatter(G.np_to_torch(src, dt).cuda(), G.idx_to_cuda(sidx), table)
+    torch.cuda.synchronize()
+    O.scatter(src, dt, sidx, host, dt)
+    got = G.torch_to_np(view, dt)
+    G.wmb.destroy_wholememory_tensor(table)
+    assert got.tobytes() == host.tobytes(), "scatter"

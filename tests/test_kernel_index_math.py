@@ -1,8 +1,10 @@
 """The division-free "vector index -> (row, vector in row)" map of the row-move kernels, checked exhaustively at the row
 boundaries on CPU.
 
-Host side (wholegraph_b200/csrc/gather_scatter.cu: set_units): magic = ceil(2^40 / units_per_row), accepted only while
-units_per_row * 32 < 2^20.  Device side (gather_scatter.cuh: row_move_vec_kernel / row_move_cvt_kernel):
+Host side (wholegraph_b200/csrc/gather_scatter.cu: set_units): magic = ceil(2^40 / units_per_row).  Only batches of
+more than one row use the map, and plan() batches rows only while batch_rows * row_bytes <= 4 KiB, so the units_per_row
+that reach it are < 2^12; the test covers every units_per_row * 32 < 2^20 (the range round 1 accepted).  Longer rows travel
+one per warp (row = 0, no map; tests/test_access_width_gpu.py::test_very_long_rows).  Device side (gather_scatter.cuh: row_move_vec_kernel / row_move_cvt_kernel):
 row = (w * magic) >> 40 for w in [0, batch_rows * units_per_row) plus up to 32 * UNROLL lanes of overshoot.
 The claim in table_ref.hpp is that this equals floor(w / units_per_row) on that whole range."""
 import numpy as np

@@ -65,6 +65,13 @@ def test_ranks_sharing_one_gpu_mapped_memory(world, scenario):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_rank_local_failures_reach_every_rank(world):
+    """A missing part file on one rank / different partitions on different ranks: every rank gets an error, none hangs."""
+    _run(world, "failing_together", share_gpu=world > 1)
+
+
+@pytest.mark.timeout(900)
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("scenario", ["gather_scatter", "gradient", "sampling", "file_io"])
 def test_one_rank_per_gpu(world, scenario):

@@ -97,7 +97,8 @@ def test_reference_cython_binding_on_our_library():
         idx = rng.integers(0, rows, size=3333).astype(np.int64)
         idx[3] = -1
         out = torch.full((3333, cols), 9.0, dtype=torch.float16, device="cuda")  # fp32 table -> fp16 output
-        rwmb.wholememory_gather_op(wm, wrap(torch.from_numpy(idx).cuda()), wrap(out), env.get_env_fns(),
+        idx_t = torch.from_numpy(idx).cuda()  # WrappedLocalTensor keeps a pointer only: hold the tensor across the call
+        rwmb.wholememory_gather_op(wm, wrap(idx_t), wrap(out), env.get_env_fns(),
                                    torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         exp = np.full((3333, cols), 9.0, dtype=np.float16)

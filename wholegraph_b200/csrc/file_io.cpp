@@ -73,56 +73,58 @@ wholememory_error_code_t wholememory_load_from_file(wholememory_handle_t h,
       WM_ERROR("input file count=%d", file_count);
       return WHOLEMEMORY_INVALID_INPUT;
     }
-    std::vector<size_t> first_entry(file_count + 1, 0); /* stream position of each file's first entry */
-    for (int i = 0; i < file_count; ++i) {
-      struct stat st {};
-      if (file_names[i] == nullptr || ::stat(file_names[i], &st) != 0 || access(file_names[i], R_OK) != 0) {
-        WM_ERROR("input_file[%d] of %d (%s) cannot open for read.", i, file_count, file_names[i] ? file_names[i] : "(null)");
-        return WHOLEMEMORY_INVALID_INPUT;
+    /* From here on a failure may be rank-local (a file one rank cannot read, a short read): it is recorded, not thrown,
+     * and the closing rendezvous tells every rank -- nobody is left waiting in a barrier for a rank that gave up. */
+    first_error err;
+    err.attempt([&] {
+      std::vector<size_t> first_entry(file_count + 1, 0); /* stream position of each file's first entry */
+      for (int i = 0; i < file_count; ++i) {
+        struct stat st {};
+        if (file_names[i] == nullptr || ::stat(file_names[i], &st) != 0 || access(file_names[i], R_OK) != 0)
+          WM_THROW(WHOLEMEMORY_INVALID_INPUT, "input_file[%d] of %d (%s) cannot open for read.", i, file_count, file_names[i] ? file_names[i] : "(null)");
+        if ((size_t)st.st_size % esz != 0)
+          WM_THROW(WHOLEMEMORY_INVALID_INPUT, "input_file[%d] of %d (%s) size=%zu is not a multiple of entry_size=%zu", i, file_count,
+                   file_names[i], (size_t)st.st_size, esz);
+        first_entry[i + 1] = first_entry[i] + (size_t)st.st_size / esz;
       }
-      if ((size_t)st.st_size % esz != 0) {
-        WM_ERROR("input_file[%d] of %d (%s) size=%zu is not a multiple of entry_size=%zu", i, file_count, file_names[i], (size_t)st.st_size, esz);
-        return WHOLEMEMORY_INVALID_INPUT;
-      }
-      first_entry[i + 1] = first_entry[i] + (size_t)st.st_size / esz;
-    }
-    const size_t table_entries = h->total_size / stride;
-    if (first_entry[file_count] > table_entries) {
-      WM_ERROR("all %d input files hold %zu entries, but the memory holds only %zu", file_count, first_entry[file_count], table_entries);
-      return WHOLEMEMORY_INVALID_VALUE;
-    }
-    require_cuda("wholememory_load_from_file");
-    const int me    = h->comm->world_rank;
-    size_t begin    = h->part_offsets[me] / stride;
-    size_t end      = std::min((h->part_offsets[me] + h->part_sizes[me]) / stride, first_entry[file_count]);
-    char* local     = static_cast<char*>(h->local_ptr);
-    const size_t per_stage = std::max<size_t>(1, kStageBytes / esz);
-    pinned_stage stage(per_stage * esz);
-    WM_EXPECT(stage.p != nullptr, WHOLEMEMORY_OUT_OF_MEMORY, "cannot allocate the %zu-byte staging buffer", per_stage * esz);
-    int file = 0;
-    for (size_t e = begin; e < end;) {
-      while (e >= first_entry[file + 1]) ++file;
-      size_t count = std::min({per_stage, end - e, first_entry[file + 1] - e});
-      int fd       = ::open(file_names[file], O_RDONLY | O_CLOEXEC);
-      WM_EXPECT(fd >= 0, WHOLEMEMORY_SYSTEM_ERROR, "open(%s): %s", file_names[file], strerror(errno));
-      size_t want = count * esz, got = 0;
-      off_t off   = (off_t)((e - first_entry[file]) * esz);
-      while (got < want) {
-        ssize_t r = ::pread(fd, stage.p + got, want - got, off + (off_t)got);
-        if (r <= 0) {
-          ::close(fd);
-          WM_THROW(WHOLEMEMORY_SYSTEM_ERROR, "short read from %s", file_names[file]);
+      const size_t table_entries = h->total_size / stride;
+      if (first_entry[file_count] > table_entries)
+        WM_THROW(WHOLEMEMORY_INVALID_VALUE, "all %d input files hold %zu entries, but the memory holds only %zu", file_count,
+                 first_entry[file_count], table_entries);
+      require_cuda("wholememory_load_from_file");
+      const int me    = h->comm->world_rank;
+      size_t begin    = h->part_offsets[me] / stride;
+      size_t end      = std::min((h->part_offsets[me] + h->part_sizes[me]) / stride, first_entry[file_count]);
+      char* local     = static_cast<char*>(h->local_ptr);
+      const size_t per_stage = std::max<size_t>(1, kStageBytes / esz);
+      pinned_stage stage(per_stage * esz);
+      WM_EXPECT(stage.p != nullptr, WHOLEMEMORY_OUT_OF_MEMORY, "cannot allocate the %zu-byte staging buffer", per_stage * esz);
+      int file = 0;
+      for (size_t e = begin; e < end;) {
+        while (e >= first_entry[file + 1]) ++file;
+        size_t count = std::min({per_stage, end - e, first_entry[file + 1] - e});
+        int fd       = ::open(file_names[file], O_RDONLY | O_CLOEXEC);
+        WM_EXPECT(fd >= 0, WHOLEMEMORY_SYSTEM_ERROR, "open(%s): %s", file_names[file], strerror(errno));
+        size_t want = count * esz, got = 0;
+        off_t off   = (off_t)((e - first_entry[file]) * esz);
+        while (got < want) {
+          ssize_t r = ::pread(fd, stage.p + got, want - got, off + (off_t)got);
+          if (r <= 0) {
+            ::close(fd);
+            WM_THROW(WHOLEMEMORY_SYSTEM_ERROR, "short read from %s", file_names[file]);
+          }
+          got += (size_t)r;
         }
-        got += (size_t)r;
+        ::close(fd);
+        char* dst = local + (e - begin) * stride + memory_offset;
+        WM_CUDA(cudaMemcpy2D(dst, stride, stage.p, esz, esz, count, cudaMemcpyDefault));
+        e += count;
       }
-      ::close(fd);
-      char* dst = local + (e - begin) * stride + memory_offset;
-      WM_CUDA(cudaMemcpy2D(dst, stride, stage.p, esz, esz, count, cudaMemcpyDefault));
-      e += count;
-    }
-    WM_INFO("rank %d loaded entries [%zu, %zu) from %d file(s)", me, begin, std::max(begin, end), file_count);
+      WM_INFO("rank %d loaded entries [%zu, %zu) from %d file(s)", me, begin, std::max(begin, end), file_count);
+    });
+    if (!err.ok()) WM_ERROR("%s", err.what.c_str());
     std::lock_guard<std::mutex> lk(h->comm->mu);
-    h->comm->boot->barrier(); /* everyone's shard is in place before anyone gathers */
+    fail_together(h->comm, err, "wholememory_load_from_file"); /* everyone's shard is in place before anyone gathers */
     return WHOLEMEMORY_SUCCESS;
   });
 }

@@ -130,10 +130,12 @@ int vec_blocks_per_sm()
   return occ;
 }
 
-/* magic multiplier for floor(w / d) = (w * magic) >> 40, exact while w < 2^20 and d < 2^20 */
+/* magic multiplier for floor(w / d) = (w * magic) >> 40, exact while w < 2^20 and d < 2^20.  Only batches of more than one
+ * row use it, and plan() batches rows only up to kBatchBytes (<= 4096 units per batch); longer rows travel one per warp
+ * and are limited only by the 32-bit unit counter (2^31 units: 2 GiB rows at 1-byte units, 64 GiB at 32-byte units). */
 void set_units(row_geom* g, int64_t units_per_row)
 {
-  WM_EXPECT(units_per_row > 0 && units_per_row * 32 < (1 << 20), WHOLEMEMORY_NOT_SUPPORTED,
+  WM_EXPECT(units_per_row > 0 && units_per_row < ((int64_t)1 << 31), WHOLEMEMORY_NOT_SUPPORTED,
             "row too long for the gather/scatter kernels (%ld units)", (long)units_per_row);
   g->units_per_row = (int)units_per_row;
   g->div_magic     = (((uint64_t)1 << 40) + (uint64_t)units_per_row - 1) / (uint64_t)units_per_row;
@@ -151,7 +153,7 @@ void plan(int64_t n, int64_t row_bytes, int sms, int blocks_per_sm, int* batch_r
   while (R > 1 && (int64_t)R * row_bytes > kBatchBytes) R >>= 1;
   while (R > 1 && n / R < total_warps * 2) R >>= 1; /* small calls: spread the rows over the whole GPU */
   static const int forced_rows = env_int("WG_BATCH_ROWS", 0);
-  if (forced_rows > 0) R = forced_rows;
+  if (forced_rows > 0 && (int64_t)forced_rows * row_bytes <= 16384) R = forced_rows; /* keeps R * units inside the magic's range */
   int64_t nbatch = (n + R - 1) / R;
   int64_t need   = (nbatch + wpc - 1) / wpc;
   *batch_rows    = R;

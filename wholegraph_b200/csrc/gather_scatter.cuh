@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(1024) row_move_vec_kernel(table_ref tref,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         uint32_t w   = w0 + (uint32_t)u * 32u + (uint32_t)lane;
-        uint32_t row = VN_CT > 0 ? w / (uint32_t)VN_CT : (uint32_t)(((uint64_t)w * magic) >> 40);
+        /* one-row batches (every row above 4 KiB) need no map at all, so the row length is not limited by the magic's range */
+        uint32_t row = VN_CT > 0 ? w / (uint32_t)VN_CT : (R == 1 ? 0u : (uint32_t)(((uint64_t)w * magic) >> 40));
         uint32_t v   = w - row * Vn;
         /* shuffles are executed by all lanes, out-of-range lanes read lane (row & 31) harmlessly */
         char* t   = shfl_ptr(trow, (int)(row & 31u));
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) row_move_cvt_kernel(table_ref tref,
     const uint32_t total = (uint32_t)R * Vn;
     for (uint32_t w0 = 0; w0 < total; w0 += 32u) {
       uint32_t w   = w0 + (uint32_t)lane;
-      uint32_t row = (uint32_t)(((uint64_t)w * magic) >> 40);
+      uint32_t row = R == 1 ? 0u : (uint32_t)(((uint64_t)w * magic) >> 40);
       uint32_t v   = w - row * Vn;
       char* t      = shfl_ptr(trow, (int)(row & 31u));
       if (w < total && t != nullptr) {

@@ -131,8 +131,7 @@ void append_unique_typed(const void* targets, int T, const void* neighbors, int 
   void* cub_tmp = cub_b.device(cub_bytes, WHOLEMEMORY_DT_INT8);
   cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, N + 1, s);
   int fresh = 0;
-  WM_CUDA(cudaMemcpyAsync(&fresh, pos + N, sizeof(int), cudaMemcpyDeviceToHost, s));
-  WM_CUDA(cudaStreamSynchronize(s));
+  read_back_sync(&fresh, pos + N, sizeof(int), s);
   KeyT* uniq = static_cast<KeyT*>(output_alloc(env, unique_ctx, (size_t)T + fresh, dt));
   if (T > 0) WM_CUDA(cudaMemcpyAsync(uniq, tg, (size_t)T * sizeof(KeyT), cudaMemcpyDeviceToDevice, s));
   if (N > 0) {

@@ -78,21 +78,20 @@ void make_partition(wholememory_handle_t h, const size_t* rank_entry_partition)
 }
 
 /* ---------------- VMM-backed device memory ---------------- */
+/* Collective.  Rule for every function that creates backing storage: a rank-local failure never skips a collective the
+ * other ranks are about to enter.  Local steps run under `attempt`, which records the first error instead of throwing;
+ * the status travels with the next collective (or with the agreement that ends create_handle) and all ranks fail together. */
 void vmm_create(wholememory_handle_t h, bool map_peers)
 {
-  require_cuda("device WholeMemory allocation");
   auto* c      = h->comm;
   const int ws = c->world_size, me = c->world_rank;
-  const auto& d = cu();
-  WM_CUDA(cudaSetDevice(c->dev_id));
   h->backing   = wholememory_handle_::backing_t::vmm;
   h->page_size = c->alloc_granularity;
   /* Mapping granule.  Large tables are laid out in 512 MiB-aligned granules (as the reference does for
    * totals >= 16 GiB, memory_handle.cpp:229-230,1686-1687) so the driver can use its largest page size
-   * and random row reads miss the TLB less.  WG_VMM_PAGE_MB overrides (developer knob). */
+   * and random row reads miss the TLB less. */
   {
-    const char* v   = getenv("WG_VMM_PAGE_MB");
-    size_t want     = (v && *v) ? (size_t)atol(v) << 20 : (h->total_size >= ((size_t)16 << 30) ? (size_t)512 << 20 : 0);
+    size_t want = h->total_size >= ((size_t)16 << 30) ? (size_t)512 << 20 : 0;
     if (want > h->page_size) h->page_size = round_up(want, c->alloc_granularity);
   }
   h->map_offsets.assign(ws, 0);
@@ -117,61 +116,69 @@ void vmm_create(wholememory_handle_t h, bool map_peers)
     h->va_size = off;
   }
   h->rank_base.assign(ws, nullptr);
-  if (h->va_size == 0) return;
-
-  WM_CU(d.MemAddressReserve(&h->va, h->va_size, page, 0, 0));
-
   const bool share = map_peers && ws > 1;
-  CUmemAllocationProp prop{};
-  prop.type                 = CU_MEM_ALLOCATION_TYPE_PINNED;
-  prop.location.type        = CU_MEM_LOCATION_TYPE_DEVICE;
-  prop.location.id          = c->dev_id;
-  prop.requestedHandleTypes = share ? CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR : CU_MEM_HANDLE_TYPE_NONE;
-  CUresult created = CUDA_SUCCESS;
-  if (h->map_sizes[me] > 0) {
-    created = d.MemCreate(&h->phys[me], h->map_sizes[me], &prop, 0);
-    if (created != CUDA_SUCCESS) h->phys[me] = 0;
-  }
-  /* An allocation failure has to be collective: a rank that left here alone would strand the others in the fd
-   * exchange below.  Everybody learns everybody's result and all ranks fail together. */
-  int failed_rank = created != CUDA_SUCCESS ? me : -1;
-  if (ws > 1) {
-    int32_t mine = (int32_t)created;
-    std::vector<int32_t> all(ws, 0);
-    c->boot->allgather(&mine, all.data(), sizeof(mine));
-    for (int r = 0; r < ws && failed_rank < 0; ++r)
-      if (all[r] != (int32_t)CUDA_SUCCESS) {
-        failed_rank = r;
-        created     = (CUresult)all[r];
+
+  /* phase A (local): device, VA range, my physical shard */
+  first_error err;
+  err.attempt([&] {
+    require_cuda("device WholeMemory allocation");
+    WM_CUDA(cudaSetDevice(c->dev_id));
+    if (h->va_size == 0) return;
+    const auto& d = cu();
+    WM_CU(d.MemAddressReserve(&h->va, h->va_size, page, 0, 0));
+    CUmemAllocationProp prop{};
+    prop.type                 = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type        = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id          = c->dev_id;
+    prop.requestedHandleTypes = share ? CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR : CU_MEM_HANDLE_TYPE_NONE;
+    if (h->map_sizes[me] > 0) {
+      CUresult created = d.MemCreate(&h->phys[me], h->map_sizes[me], &prop, 0);
+      if (created != CUDA_SUCCESS) {
+        h->phys[me] = 0;
+        if (created == CUDA_ERROR_OUT_OF_MEMORY)
+          WM_THROW(WHOLEMEMORY_OUT_OF_MEMORY, "cuMemCreate(%zu bytes) out of device memory on rank %d", h->map_sizes[me], me);
+        WM_THROW(WHOLEMEMORY_CUDA_ERROR, "cuMemCreate(%zu bytes) failed on rank %d: CUDA driver error %d (%s)", h->map_sizes[me], me,
+                 (int)created, cu_error_string(created));
       }
-  }
-  if (failed_rank >= 0) {
-    if (created == CUDA_ERROR_OUT_OF_MEMORY)
-      WM_THROW(WHOLEMEMORY_OUT_OF_MEMORY, "cuMemCreate(%zu bytes) out of device memory on rank %d", h->map_sizes[failed_rank], failed_rank);
-    WM_THROW(WHOLEMEMORY_CUDA_ERROR, "cuMemCreate(%zu bytes) failed on rank %d: CUDA driver error %d (%s)", h->map_sizes[failed_rank],
-             failed_rank, (int)created, cu_error_string(created));
-  }
+    }
+  });
+  fail_together(c, err, "device memory allocation"); /* collective 1 */
+  if (h->va_size == 0) return;
+  const auto& d = cu();
+
+  /* phase B: my shard's fd to everyone (collective 2 runs even when my export failed: fd -1) */
   if (share) {
     int my_fd = -1;
-    if (h->phys[me] != 0)
-      WM_CU(d.MemExportToShareableHandle(&my_fd, h->phys[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    err.attempt([&] {
+      if (h->phys[me] != 0)
+        WM_CU(d.MemExportToShareableHandle(&my_fd, h->phys[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    });
     std::vector<int> fds = c->boot->allgather_fds(my_fd);
     if (my_fd >= 0) ::close(my_fd);
     for (int r = 0; r < ws; ++r) {
-      if (r != me && fds[r] >= 0 && h->map_sizes[r] > 0)
-        WM_CU(d.MemImportFromShareableHandle(&h->phys[r], (void*)(uintptr_t)fds[r], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+      if (r != me && h->map_sizes[r] > 0) {
+        if (fds[r] < 0) err.attempt([&] { WM_THROW(WHOLEMEMORY_CUDA_ERROR, "rank %d could not export its shard", r); });
+        else
+          err.attempt([&] {
+            WM_CU(d.MemImportFromShareableHandle(&h->phys[r], (void*)(uintptr_t)fds[r], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+          });
+      }
       if (fds[r] >= 0) ::close(fds[r]);
     }
   }
-  CUmemAccessDesc acc{};
-  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  acc.location.id   = c->dev_id;
-  acc.flags         = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  for (int r = 0; r < ws; ++r) {
-    if (h->phys[r] == 0) continue;
-    WM_CU(d.MemMap(h->va + h->map_offsets[r], h->map_sizes[r], 0, h->phys[r], 0));
-    WM_CU(d.MemSetAccess(h->va + h->map_offsets[r], h->map_sizes[r], &acc, 1));
-  }
+  /* phase C (local): map and open every shard; a failure here is reported by the agreement that ends create_handle */
+  err.attempt([&] {
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id   = c->dev_id;
+    acc.flags         = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    for (int r = 0; r < ws; ++r) {
+      if (h->phys[r] == 0) continue;
+      WM_CU(d.MemMap(h->va + h->map_offsets[r], h->map_sizes[r], 0, h->phys[r], 0));
+      WM_CU(d.MemSetAccess(h->va + h->map_offsets[r], h->map_sizes[r], &acc, 1));
+    }
+  });
+  err.rethrow();
   char* base = reinterpret_cast<char*>(h->va);
   if (h->type == WHOLEMEMORY_MT_CONTINUOUS) {
     h->flat_base = base;
@@ -201,18 +208,24 @@ void vmm_destroy(wholememory_handle_t h) noexcept
 /* ---------------- shared host segment ---------------- */
 void host_shared_create(wholememory_handle_t h)
 {
-  require_cuda("host WholeMemory allocation (cudaHostRegister)");
   auto* c    = h->comm;
   h->backing = wholememory_handle_::backing_t::host_shared;
   h->rank_base.assign(c->world_size, nullptr);
   if (h->total_size == 0) return;
+  /* rank 0's failure to create the segment travels as fd -1: every rank still runs the fd exchange and all of them
+   * fail on "no shared segment"; later rank-local failures (mmap, cudaHostRegister) reach the others through the
+   * agreement that ends create_handle */
   int fd = -1;
-  if (c->world_rank == 0) {
+  first_error err;
+  err.attempt([&] { require_cuda("host WholeMemory allocation (cudaHostRegister)"); });
+  if (c->world_rank == 0 && err.ok()) {
     fd = memfd_create("wgb200_host_wm", MFD_CLOEXEC);
-    WM_EXPECT(fd >= 0, WHOLEMEMORY_SYSTEM_ERROR, "memfd_create: %s", strerror(errno));
-    if (ftruncate(fd, (off_t)h->total_size) != 0) {
+    if (fd < 0) {
+      WM_ERROR("memfd_create: %s", strerror(errno));
+    } else if (ftruncate(fd, (off_t)h->total_size) != 0) {
+      WM_ERROR("ftruncate(%zu): %s", h->total_size, strerror(errno));
       ::close(fd);
-      WM_THROW(WHOLEMEMORY_OUT_OF_MEMORY, "ftruncate(%zu): %s", h->total_size, strerror(errno));
+      fd = -1;
     }
   }
   std::vector<int> fds = c->boot->allgather_fds(fd);
@@ -220,7 +233,8 @@ void host_shared_create(wholememory_handle_t h)
   int seg = fds[0];
   for (size_t r = 1; r < fds.size(); ++r)
     if (fds[r] >= 0) ::close(fds[r]);
-  WM_EXPECT(seg >= 0, WHOLEMEMORY_SYSTEM_ERROR, "no shared segment fd received");
+  err.rethrow();
+  WM_EXPECT(seg >= 0, WHOLEMEMORY_SYSTEM_ERROR, "no shared segment fd received (rank 0 could not create it)");
   void* p = mmap(nullptr, h->total_size, PROT_READ | PROT_WRITE, MAP_SHARED, seg, 0);
   ::close(seg);
   WM_EXPECT(p != MAP_FAILED, WHOLEMEMORY_SYSTEM_ERROR, "mmap(%zu): %s", h->total_size, strerror(errno));
@@ -312,6 +326,22 @@ void release_storage(wholememory_handle_t h) noexcept
 
 }  // namespace
 
+/* every rank learns every rank's status; all throw the first failure (lowest rank) */
+void fail_together(wholememory_comm_t c, const first_error& mine, const char* stage)
+{
+  if (c->world_size == 1) {
+    mine.rethrow();
+    return;
+  }
+  int32_t code = (int32_t)mine.code;
+  std::vector<int32_t> all(c->world_size, 0);
+  c->boot->allgather(&code, all.data(), sizeof(code));
+  mine.rethrow(); /* my own failure carries the detailed message */
+  for (int r = 0; r < c->world_size; ++r)
+    if (all[r] != (int32_t)WHOLEMEMORY_SUCCESS)
+      WM_THROW((wholememory_error_code_t)all[r], "%s failed on rank %d (see that rank's log)", stage, r);
+}
+
 wholememory_error_code_t create_handle(wholememory_handle_t* out,
                                        size_t total_size,
                                        wholememory_comm_t comm,
@@ -374,7 +404,8 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
   h->total_size  = total_size;
   h->granularity = granularity;
   make_partition(h.get(), rank_entry_partition);
-  try {
+  first_error err;
+  err.attempt([&] {
     if (location == WHOLEMEMORY_ML_DEVICE) {
       bool map_peers = true;
       if (type == WHOLEMEMORY_MT_DISTRIBUTED)
@@ -386,11 +417,16 @@ wholememory_error_code_t create_handle(wholememory_handle_t* out,
       host_shared_create(h.get());
     }
     build_public_gref(h.get());
+  });
+  /* Everyone mapped before anyone touches a peer -- and everyone learns whether everyone succeeded: a rank whose import,
+   * map or registration failed takes all ranks out together instead of leaving them with a handle it does not have.
+   * (Failures that vmm_create / host_shared_create already made collective arrive here on every rank at once.) */
+  try {
+    fail_together(comm, err, "WholeMemory allocation");
   } catch (...) {
     release_storage(h.get());
     throw;
   }
-  comm->boot->barrier(); /* everyone mapped before anyone touches a peer */
   comm->handles[h->id] = h.get();
   obj_register(OBJ_HANDLE, h.get());
   *out                 = h.release();

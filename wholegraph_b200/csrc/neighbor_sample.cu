@@ -253,8 +253,7 @@ void run_sampler(const csr_ref& g, const void* centers, int n, int k, uint64_t s
   void* cub_tmp = cub_b.device(cub_bytes, WHOLEMEMORY_DT_INT8);
   cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, offsets, n + 1, s);
   int total = 0;
-  WM_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  WM_CUDA(cudaStreamSynchronize(s)); /* the output allocation callback needs the size */
+  read_back_sync(&total, offsets + n, sizeof(int), s); /* the output allocation callback needs the size */
 
   ColT* out_dst   = static_cast<ColT*>(output_alloc(env, dst_ctx, (size_t)total, col_dtype));
   int* out_lid    = lid_ctx ? static_cast<int*>(output_alloc(env, lid_ctx, (size_t)total, WHOLEMEMORY_DT_INT)) : nullptr;

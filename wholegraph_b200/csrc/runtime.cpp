@@ -118,6 +118,26 @@ int sm_count(int dev)
   return p ? p->multiProcessorCount : 148;
 }
 
+void read_back_sync(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t s)
+{
+  constexpr size_t kStage = 256;
+  thread_local void* stage = nullptr; /* lives as long as the thread; a few hundred bytes of pinned memory */
+  if (bytes <= kStage && stage == nullptr) {
+    if (cudaMallocHost(&stage, kStage) != cudaSuccess) {
+      (void)cudaGetLastError();
+      stage = nullptr;
+    }
+  }
+  if (bytes <= kStage && stage != nullptr) {
+    WM_CUDA(cudaMemcpyAsync(stage, dev_src, bytes, cudaMemcpyDeviceToHost, s));
+    WM_CUDA(cudaStreamSynchronize(s));
+    memcpy(host_dst, stage, bytes);
+    return;
+  }
+  WM_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, s));
+  WM_CUDA(cudaStreamSynchronize(s));
+}
+
 static std::mutex g_init_mu;
 static bool g_inited = false;
 

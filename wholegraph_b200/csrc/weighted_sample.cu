@@ -259,8 +259,7 @@ void run_weighted(const csr_ref& g, const table_ref& weights, int64_t weight_off
   void* cub_tmp = cub_b.device(cub_bytes, WHOLEMEMORY_DT_INT8);
   cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, offsets, n + 1, s);
   int total = 0;
-  WM_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  WM_CUDA(cudaStreamSynchronize(s));
+  read_back_sync(&total, offsets + n, sizeof(int), s);
   ColT* out_dst    = static_cast<ColT*>(output_alloc(env, dst_ctx, (size_t)total, col_dtype));
   int* out_lid     = lid_ctx ? static_cast<int*>(output_alloc(env, lid_ctx, (size_t)total, WHOLEMEMORY_DT_INT)) : nullptr;
   int64_t* out_gid = gid_ctx ? static_cast<int64_t*>(output_alloc(env, gid_ctx, (size_t)total, WHOLEMEMORY_DT_INT64)) : nullptr;
@@ -281,8 +280,7 @@ void run_weighted(const csr_ref& g, const table_ref& weights, int64_t weight_off
   overfull_degree_kernel<IdT><<<(n + 1 + 127) / 128, 128, 0, s>>>(g, cen, n, k, seg_len);
   cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, seg_len, seg_off, n + 1, s);
   int nkeys = 0;
-  WM_CUDA(cudaMemcpyAsync(&nkeys, seg_off + n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  WM_CUDA(cudaStreamSynchronize(s));
+  read_back_sync(&nkeys, seg_off + n, sizeof(int), s);
   int* sorted_idx = nullptr;
   if (nkeys > 0) {
     float* ka = static_cast<float*>(keys_a.device((size_t)nkeys, WHOLEMEMORY_DT_FLOAT));

@@ -250,6 +250,36 @@ bool live(wholememory_tensor_t t);           /* tensor alive and, when WholeMemo
     }                                                                                               \
   } while (0)
 
+/* ------------------------------------------------------------------ failing together
+ * A rank-local failure inside a collective operation never skips a collective the other ranks are about to enter: local
+ * steps run under first_error::attempt (records instead of throwing), the status then travels with fail_together() and
+ * every rank throws the first failure. */
+struct first_error {
+  wholememory_error_code_t code = WHOLEMEMORY_SUCCESS;
+  std::string what;
+  bool ok() const { return code == WHOLEMEMORY_SUCCESS; }
+  template <typename F>
+  void attempt(F&& fn)
+  {
+    if (!ok()) return;
+    try {
+      fn();
+    } catch (const error& e) {
+      code = e.code;
+      what = e.what();
+    } catch (const std::exception& e) {
+      code = WHOLEMEMORY_UNKNOW_ERROR;
+      what = e.what();
+    }
+  }
+  void rethrow() const
+  {
+    if (!ok()) throw error(code, what);
+  }
+};
+
+void fail_together(wholememory_comm_t c, const first_error& mine, const char* stage); /* collective; memory_handle.cpp */
+
 /* ------------------------------------------------------------------ runtime helpers */
 wholememory_error_code_t create_handle(wholememory_handle_t* out,
                                        size_t total_size,
@@ -302,5 +332,10 @@ void* output_alloc(wholememory_env_func_t* env,
                    wholememory_memory_allocation_type_t kind = WHOLEMEMORY_MA_DEVICE);
 
 int sm_count(int dev = -1);
+
+/* Small device->host read-back (op output sizes) through a per-thread page-locked staging word: a D2H copy into pageable
+ * memory goes through the driver's bounce buffer and costs 10-15 us more than the copy itself.  Copies, then waits for the
+ * stream. */
+void read_back_sync(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t s);
 
 }  // namespace wm
