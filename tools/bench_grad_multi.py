@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--grads", type=int, default=262144)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--zipf", type=float, default=0.0, help="> 1: ids drawn Zipf(a) over the rows (hot rows, duplicates) instead of uniform")
     args = ap.parse_args()
     rank, world, local_rank = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local_rank)
@@ -47,7 +48,14 @@ def main():
     g = torch.Generator(device="cuda")
     g.manual_seed(100 + rank)
     grads = torch.randn(args.grads, args.dim, device="cuda", generator=g)
-    idxs = [torch.randint(0, rows, (args.grads,), device="cuda", generator=g) for _ in range(4)]
+    if args.zipf > 1.0:
+        import numpy as np
+        nrng = np.random.default_rng(100 + rank)
+        # hot rows spread over the whole table (a fixed odd multiplier scatters the small Zipf values across all owners)
+        idxs = [torch.from_numpy(((nrng.zipf(args.zipf, size=args.grads).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) % np.uint64(rows)).astype(np.int64)).cuda()
+                for _ in range(4)]
+    else:
+        idxs = [torch.randint(0, rows, (args.grads,), device="cuda", generator=g) for _ in range(4)]
     w_g = wrap_torch_tensor(grads)
     w_i = [wrap_torch_tensor(i) for i in idxs]
     env = get_wholegraph_env_fns()
@@ -74,7 +82,8 @@ def main():
         ms = float(ms.item())
         row_bytes = args.dim * 4
         print(json.dumps({"op": "gradient apply (LazyAdam)", "n_gpus": world, "push": os.environ.get("WG_GRAD_PUSH", "1") != "0",
-                          "grads_per_rank": args.grads, "dim": args.dim, "ms_per_step": round(ms, 4),
+                          "grads_per_rank": args.grads, "dim": args.dim, "rows_total": rows, "ids": "zipf(%g)" % args.zipf if args.zipf > 1.0 else "uniform",
+                          "unique_ids_rank0_batch0": int(torch.unique(idxs[0]).numel()), "ms_per_step": round(ms, 4),
                           "Mrows_per_s_total": round(args.grads * world / ms / 1e3, 2),
                           "grad_GBps_per_gpu": round(args.grads * row_bytes / ms / 1e6, 1)}))
     wgth.destroy_wholememory_optimizer(opt)
