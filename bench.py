@@ -164,6 +164,12 @@ SHAPES = {
     "c3": {"rows_per_gpu": 125_000_000, "dim": 128, "dtype": "fp16", "name": "C3: 125M rows/GPU x 128 fp16 (256 B rows; 1B rows at N=8)"},
 }
 NVLINK_MEASURED_GBS = 770.0  # peer copy per direction measured on this pool (B200_PROFILING.md); nominal 900
+# ncu NVLink counters of this kernel (profiles/r2_nvlink_counters.txt): a peer load puts 1.125 bytes per payload byte on the
+# reader's RX side (16 B response header per 128 B) and 0.1875 on its TX side (24 B request per 128 B); one-directional reads
+# fill the link at 880 GB/s raw = 783 GB/s of payload.  When every GPU reads from every other GPU, each direction carries
+# both: payload <= 880 / 1.3125 = 670.6 GB/s per direction -- the ceiling of the all-to-all gather, whatever the kernel does.
+NVLINK_RAW_GBS = 880.0
+NVLINK_WIRE_BYTES_PER_PAYLOAD_BYTE_ALL_TO_ALL_READS = 1.3125
 
 
 def traffic_from_profile(shape_key):
@@ -203,6 +209,9 @@ def roofline(world, n, row, ms, impl, shape_key):
             "frac_of_nominal_900": round(ingress / 900.0, 4), "traffic": None, "traffic_source": None,
             "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md: 770 GB/s; nominal NVLink 5 = 900 GB/s)",
             "what": "NVLink ingress per GPU = the (N-1)/N of the gathered rows that live on peers / kernel time",
+            "protocol_ceiling": round(NVLINK_RAW_GBS / NVLINK_WIRE_BYTES_PER_PAYLOAD_BYTE_ALL_TO_ALL_READS, 1),
+            "frac_of_protocol_ceiling": round(ingress / (NVLINK_RAW_GBS / NVLINK_WIRE_BYTES_PER_PAYLOAD_BYTE_ALL_TO_ALL_READS), 4),
+            "protocol_ceiling_source": "profiles/r2_nvlink_counters.txt: 880 GB/s raw link rate / 1.3125 wire bytes per payload byte when all GPUs read at once",
             "kernel": kernel, "kernel_ms": round(ms, 4), "bound_ms": round(max(t_nvl, t_hbm) * 1e3, 4),
             "hbm_algorithmic_gbs": round(alg_gbs, 2), "hbm_frac": round(alg_gbs / hbm_peak, 4), "remote_bytes_per_launch": int(remote_bytes),
             "algorithmic_bytes_per_launch": alg_bytes}
