@@ -125,3 +125,91 @@ def test_all_gradients_on_one_row_sum_in_arrival_order():
     assert not got[np.arange(rows) != 17].any()
     emb.destroy_embedding()
     opt.destroy_optimizer()
+
+
+@pytest.mark.parametrize("kind,params", [("sgd", {"weight_decay": 0.02}), ("adam", {"weight_decay": 0.01, "beta1": 0.85}), ("adagrad", {}), ("rmsprop", {"alpha": 0.9})])
+@pytest.mark.parametrize("dim", [4, 127, 512, 1028])
+def test_hot_rows_take_the_long_run_kernel(kind, params, dim):
+    """Rows with more than 64 gradients in one step are merged by long_run_update_kernel (a CTA per run, deep prefetch, same
+    arrival-order sum).  Run lengths on both sides of the threshold and of its multiples (64, 65, 128, 129, 1000, 5000), heads
+    at every alignment relative to the 64-position grid, mixed with short runs and singletons, two steps; results within
+    1e-5 of the oracle like every other optimizer case, and SGD's merged sum bit-exact (additions only)."""
+    import gpu_utils as G
+    import wholegraph_b200.binding as wmb
+    from wholegraph_b200.torch.wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
+    comm = G.single_comm()
+    rows = 4000
+    rng = np.random.default_rng(dim)
+    d = wmb.PyWholeMemoryTensorDescription()
+    d.set_dtype(wmb.DtFloat)
+    d.set_shape((rows, dim))
+    d.set_stride((dim, 1))
+    emb = wmb.create_embedding(d, comm, wmb.MtChunked, wmb.MlDevice, wmb.create_non_cache_policy())
+    opt = wmb.create_optimizer({"sgd": wmb.OptSgd, "adam": wmb.OptLazyAdam, "adagrad": wmb.OptAdaGrad, "rmsprop": wmb.OptRmsProp}[kind], params)
+    opt.add_embedding(emb)
+    local, _ = emb.get_embedding_tensor().get_local_tensor(wmb.MlDevice, 0)
+    w = rng.standard_normal((rows, dim)).astype(np.float32)
+    local.copy_(torch.from_numpy(w))
+    m, v, b12 = np.zeros_like(w), np.zeros_like(w), np.ones((rows, 2), np.float32)
+    env = get_wholegraph_env_fns()
+    try:
+        for step in range(2):
+            runs = {7: 64, 8: 65, 100: 128, 101: 129, 900: 1000, 2500: 5000, 3999: 63, 0: 66}   # row id -> number of gradients
+            ids = np.concatenate([np.full(c, r, np.int64) for r, c in runs.items()] + [rng.integers(0, rows, size=37 + step).astype(np.int64)])
+            rng.shuffle(ids)   # arrival order is arbitrary; the sort is stable
+            # magnitudes in [0.01, 1]: sums of thousands of rows stay small enough that cancellation in w - lr * g does not turn
+            # the one-ulp FMA differences between nvcc and the C oracle into relative errors above the 1e-5 bar
+            g = (rng.standard_normal((ids.size, dim)) * np.float32(10.0) ** rng.integers(-2, 1, size=(ids.size, 1))).astype(np.float32)
+            idx_t, g_t = torch.from_numpy(ids).cuda(), torch.from_numpy(g).cuda()
+            wmb.EmbeddingGatherGradientApply(emb, wrap_torch_tensor(idx_t), wrap_torch_tensor(g_t), False, 0.05, env, get_stream())
+            urows, ug = O.dedup_gradients(ids, g)
+            kw = dict(weight_decay=params.get("weight_decay", 0.0), epsilon=params.get("epsilon", 1e-8))
+            if kind == "adam":
+                O.optimizer_step("adam", w, urows, ug, 0.05, state=(m, v), b12=b12, beta1=params.get("beta1", 0.9), **kw)
+            elif kind == "sgd":
+                O.optimizer_step("sgd", w, urows, ug, 0.05, weight_decay=kw["weight_decay"])
+            elif kind == "adagrad":
+                O.optimizer_step("adagrad", w, urows, ug, 0.05, state=m, **kw)
+            else:
+                O.optimizer_step("rmsprop", w, urows, ug, 0.05, state=m, alpha=params.get("alpha", 0.99), **kw)
+        torch.cuda.synchronize()
+        got = local.cpu().numpy()
+        assert np.allclose(got, w, rtol=1e-5, atol=1e-5), f"{kind} dim={dim}: max abs err {np.abs(got - w).max()} in rows {np.unique(np.argwhere(~np.isclose(got, w, rtol=1e-5, atol=1e-5))[:, 0])[:10]}"
+        if kind == "adam":
+            bt = emb.get_optimizer_state("beta12t").get_local_tensor(wmb.MlDevice, 0)[0].cpu().numpy()
+            assert np.allclose(bt, b12, rtol=1e-6, atol=0), "per-row beta^t state differs"
+    finally:
+        emb.destroy_embedding()
+        opt.destroy_optimizer()
+
+
+def test_five_thousand_gradients_on_one_row_sum_bit_exactly():
+    """The long-run kernel keeps the sequential left-to-right sum: SGD with lr 1 and w 0 returns minus that sum, bit for bit."""
+    import gpu_utils as G
+    import wholegraph_b200.binding as wmb
+    from wholegraph_b200.torch.wholegraph_env import get_stream, get_wholegraph_env_fns, wrap_torch_tensor
+    comm = G.single_comm()
+    rows, dim, n = 64, 516, 5000   # 516 floats: a second column pass for 4 of the 128 threads
+    rng = np.random.default_rng(44)
+    d = wmb.PyWholeMemoryTensorDescription()
+    d.set_dtype(wmb.DtFloat)
+    d.set_shape((rows, dim))
+    d.set_stride((dim, 1))
+    emb = wmb.create_embedding(d, comm, wmb.MtContinuous, wmb.MlDevice, wmb.create_non_cache_policy())
+    opt = wmb.create_optimizer(wmb.OptSgd, {})
+    opt.add_embedding(emb)
+    local, _ = emb.get_embedding_tensor().get_local_tensor(wmb.MlDevice, 0)
+    local.zero_()
+    g = (rng.standard_normal((n, dim)) * np.float32(10.0) ** rng.integers(-3, 4, size=(n, 1))).astype(np.float32)
+    idx = np.full(n, 17, np.int64)
+    idx_t, g_t = torch.from_numpy(idx).cuda(), torch.from_numpy(g).cuda()
+    wmb.EmbeddingGatherGradientApply(emb, wrap_torch_tensor(idx_t), wrap_torch_tensor(g_t), False, 1.0, get_wholegraph_env_fns(), get_stream())
+    torch.cuda.synchronize()
+    acc = np.zeros(dim, np.float32)
+    for i in range(n):
+        acc = acc + g[i]
+    got = local.cpu().numpy()
+    assert got[17].tobytes() == (np.float32(0) - acc).astype(np.float32).tobytes()
+    assert not got[np.arange(rows) != 17].any()
+    emb.destroy_embedding()
+    opt.destroy_optimizer()

@@ -20,7 +20,6 @@ def native():
     if not wenv.load_native_env():
         pytest.skip("wholegraph_b200_torch_ext is not built")
     yield wenv.torch_cpp_ext_lib
-    wenv.unload_native_env()
 
 
 def _env_table(addr):

@@ -66,8 +66,11 @@ def main():
         emb = wgth.create_embedding(comm, "distributed", "cuda", torch.float32, [rows, dim])
         opt = wgth.create_wholememory_optimizer(emb, "adam", {}, global_comm=comm)
         grads = torch.randn(n, dim, device="cuda")
+        import numpy as np
+        zipf = torch.from_numpy(((np.random.default_rng(5).zipf(1.05, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) % np.uint64(rows)).astype(np.int64)).cuda()
         for name, idx in (("uniform", torch.randint(0, rows, (n,), device="cuda", generator=g)),
-                          ("unique", torch.randperm(rows, device="cuda", generator=g)[:n].contiguous())):
+                          ("unique", torch.randperm(rows, device="cuda", generator=g)[:n].contiguous()),
+                          ("zipf(1.05): hottest row gets %d gradients" % int(torch.bincount(zipf).max().item()), zipf)):
             w_i, w_g = wrap_torch_tensor(idx), wrap_torch_tensor(grads)
             uniq = int(torch.unique(idx).numel())
 

@@ -30,6 +30,7 @@ constexpr int kPushWarps = 8;
 
 struct push_dest {
   int nranks;
+  int64_t first_logical; /* grouped position the grid starts at: bucket (me + 1) % ws, see push_rows_to_owners */
   int64_t bucket_start[kMaxInlineRanks + 1]; /* grouped order: bucket r is [bucket_start[r], bucket_start[r+1]) */
   int64_t dest_row[kMaxInlineRanks];         /* first row of MY block inside owner r's stage */
   int64_t* ids[kMaxInlineRanks];             /* owner r's id array (mapped here) */
@@ -45,9 +46,14 @@ __global__ void __launch_bounds__(kPushWarps * 32) push_rows_kernel(const IdxT* 
                                                                     int dim,
                                                                     push_dest d)
 {
-  const int lane  = threadIdx.x & 31;
-  const int64_t j = (int64_t)blockIdx.x * kPushWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  int64_t j      = (int64_t)blockIdx.x * kPushWarps + (threadIdx.x >> 5);
   if (j >= n_send) return;
+  /* the grid walks the owner buckets ROTATED: rank `me` starts with owner me + 1 and ends with itself, so at any moment the
+   * ranks of the box store into different owners instead of all flooding owner 0, then owner 1, ... (one ingress link busy,
+   * the others idle: measured 3.05 ms for the whole step at 8 GPUs, slower than the NCCL all-to-all's 2.43 ms) */
+  j += d.first_logical;
+  if (j >= n_send) j -= n_send;
   const int64_t src_row = origin[j];
   const IdxT id         = grouped_idx[j];
   int r = 0;
@@ -157,6 +163,7 @@ int64_t push_rows_to_owners(push_stage* st,
       d.rows[r]     = stage_rows(*st, r, b);
     }
     d.bucket_start[ws] = acc;
+    d.first_logical    = d.bucket_start[(me + 1) % ws];
     const bool vec4 = dim % 4 == 0 && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(rows_in) & 15) == 0;
     const unsigned grid = (unsigned)((p.n_send + kPushWarps - 1) / kPushWarps);
     const bool idx64    = p.idx_dtype == WHOLEMEMORY_DT_INT64;
