@@ -10,16 +10,20 @@
  *   gather / scatter / partition : pinned -- against the reference tests' closed-form table pattern
  *       (cpp/tests/wholememory_ops/embedding_test_utils.cu:197-238) in tests/test_oracle.py, against an
  *       independent numpy restatement, and against the reference's own GPU kernels rebuilt from
- *       /root/reference (oracle/_ref/libwholegraph_ref.so) on the GPU box (tests/test_ref_parity.py).
+ *       /root/reference (oracle/_ref/libwholegraph_ref.so) on the GPU box (tests/test_ref_parity_gpu.py) and their committed
+ *       golden outputs (tests/golden/reference_gather_scatter_golden.npz, tests/test_golden.py).
  *   sparse optimizers            : restated from the kernels; pinned on CPU against the reference's own CPU test model
  *       compiled as code (class CPUOptimizer, cpp/tests/wholememory_ops/wholememory_embedding_gradient_apply_tests.cu:169-371,
  *       built by oracle/build_ref_host_optimizer_model.sh): bit-identical over multi-step schedules with duplicate ids
  *       (tests/test_ref_optimizer_model.py); the asserted tolerance stays the reference's own 1e-5 (:481-501).  The
- *       reference's optimizer kernels also build into oracle/_ref (RAFT stubbed by a declaration); the GPU comparison
- *       with them (tests/test_zz_ref_optimizer_parity_gpu.py) has not run on a B200 yet.
+ *       reference's optimizer kernels also build into oracle/_ref (RAFT stubbed by a declaration): the three-way GPU
+ *       comparison (tests/test_zz_ref_optimizer_parity_gpu.py) is green on a B200 and their outputs are committed as
+ *       tests/golden/reference_optimizer_golden.npz, which tests/test_golden_more.py holds this oracle to on CPU.
  *   neighbor sampler             : the selection algorithms are pinned against the reference's CPU models compiled as
  *       code (cpp/tests/wholegraph_ops/graph_sampling_test_utils.cu:419-505 and :676-763, built by
- *       oracle/build_ref_host_sampling_model.sh; tests/test_ref_sampling_model.py, element for element).  The RANDOM
+ *       oracle/build_ref_host_sampling_model.sh; tests/test_ref_sampling_model.py, element for element) and against the
+ *       reference's sampler KERNELS run on a restated generator (tests/test_zz_ref_sampling_parity_gpu.py, golden outputs in
+ *       tests/golden/reference_sampler_golden.npz).  The RANDOM
  *       STREAM (RAFT PCGenerator, un-vendored dependency rapidsai/raft branch-24.12) is restated from the published
  *       PCG-XSH-RR 64/32 algorithm and checked against the pcg32 known-answer vector, not against RAFT itself:
  *       "parity unpinned" for the stream (no RAFT source / golden here).
