@@ -240,6 +240,17 @@ static std::vector<variant> variant_set(const std::string& set, int64_t row_byte
     for (int p : {1, 2, 3, 4}) add(("stpol" + std::to_string(p)).c_str(), [&](variant& v) { v.policy = p << 4; });
     add("bulk4k", [](variant& v) { v.bulk = 1; });
   }
+  if (set == "plan") { /* around the shipped plan (128 threads, ~4 KiB batches, 32-byte units, PDL), on bench-sized tables */
+    vs.clear();
+    for (int R : {2, 4, 8, 16, 32})
+      for (int th : {64, 128, 256}) {
+        if ((int64_t)R * row_bytes > 32768) continue;
+        add(("v32_pdl_R" + std::to_string(R) + "_th" + std::to_string(th)).c_str(), [&](variant& v) { v.vec = 32; v.pdl = 1; v.R = R; v.threads = th; });
+      }
+    add("v32_pdl_R4_th128_u8", [](variant& v) { v.vec = 32; v.pdl = 1; v.R = 4; v.threads = 128; v.unroll = 8; });
+    add("v32_pdl_R8_th128_u2", [](variant& v) { v.vec = 32; v.pdl = 1; v.R = 8; v.threads = 128; v.unroll = 2; });
+    add("v16_pdl_R8_th128", [](variant& v) { v.vec = 16; v.pdl = 1; v.R = 8; v.threads = 128; });
+  }
   if (set == "link" || set == "all") {
     add("ldpol0", [](variant& v) { v.policy = 0; });
     add("ldpol1_nc", [](variant& v) { v.policy = 1; });
