@@ -24,6 +24,13 @@ declare -A REFSO=([host_diff_test]=ref_host_tensor.so [ops_validation_diff]=ref_
 for t in host_diff_test ops_validation_diff graph_validation_diff; do
   [ -f "$ROOT/oracle/_ref/${REFSO[$t]}" ] || { echo "$t: skipped (oracle/_ref/${REFSO[$t]} not built)"; continue; }
   g++ -std=c++17 $SAN -I"$ROOT/include" -I/usr/local/cuda/include "$ROOT/tests/cpp/$t.cpp" -o "$OUT/$t" -ldl
-  "$OUT/$t" "$OUT/libwholegraph.so" "$ROOT/oracle/_ref/${REFSO[$t]}" 50000 2>&1 | tail -1
+  # LD_LIBRARY_PATH: the reference host code's own NEEDED libwholegraph.so must resolve to THIS sanitized build (one copy in the
+  # process: handles are checked against the issuing library's live-object registry)
+  LD_LIBRARY_PATH="$OUT" "$OUT/$t" "$OUT/libwholegraph.so" "$ROOT/oracle/_ref/${REFSO[$t]}" 50000 2>&1 | tail -1
 done
+# the control plane under load (shared-memory mailbox + sockets, intruders) and the stale-handle walk, same sanitized library
+g++ -std=c++17 $SAN -I"$ROOT/include" -I/usr/local/cuda/include -I"$CS" "$ROOT/tests/cpp/bootstrap_stress.cpp" -o "$OUT/bootstrap_stress" -L"$OUT" -lwholegraph \
+  -Wl,-rpath,"$OUT" -L/usr/local/cuda/lib64 -lcudart
+WG_BOOTSTRAP_TIMEOUT_S=120 "$OUT/bootstrap_stress" 4 2000 2>&1 | tail -1
+WG_BOOTSTRAP_TIMEOUT_S=120 "$OUT/bootstrap_stress" 3 200 1 2>&1 | tail -1
 echo "asan/ubsan host check: clean"
