@@ -294,18 +294,24 @@ def run_shape(ctx, key, shape, args, headline):
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # the reference bench's own clock: wall time over K calls + one sync
     sync_all()
     ms = ev0.elapsed_time(ev1) / args.steps
+    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
     clocks = None
-    if sampler:
-        # keep the GPU busy a little longer so the clock sampler sees the loaded state even for tiny K
-        t_end = time.time() + 1.0
-        k = 0
-        while time.time() < t_end:
+    if headline:
+        # keep the GPUs busy ~1 s longer so the clock sampler sees the loaded state even for tiny K.  EVERY rank runs the SAME
+        # number of extra steps (derived from the max-over-ranks time): on DISTRIBUTED memory without peer mapping -- and always
+        # with the reference library -- the gather is a collective call, and a rank issuing more of them than its peers hangs
+        extra = max(1, min(5000, int(1000.0 / max(ms_max, 1e-3))))
+        for k in range(extra):
             step(k)
-            k += 1
         torch.cuda.synchronize()
-        clocks = sampler.summary()
+        if sampler:
+            clocks = sampler.summary()
+        sync_all()
 
-    if args.per_step_events and rank == 0:
+    if args.per_step_events and rank == 0 and mem_type != "distributed":
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for i, (a, b) in enumerate(evs):
             a.record(stream)
@@ -314,10 +320,6 @@ def run_shape(ctx, key, shape, args, headline):
         torch.cuda.synchronize()
         per = sorted(a.elapsed_time(b) for a, b in evs)
         print("%s per-step kernel ms: min %.4f median %.4f max %.4f (loop mean %.4f)" % (key, per[0], per[len(per) // 2], per[-1], ms), file=sys.stderr)
-    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
 
     # ---- end to end (headline only): indices from pinned host, rows back to pinned host, both copies inside the timed region
     e2e = None
