@@ -13,10 +13,11 @@
  *    broadcast with shuffles.  The reference redoes the 64-bit divide in all 32 lanes of every row.
  *    Chunk bases live in kernel parameters (constant bank), not in a device table, so resolving
  *    needs no dependent global load.
- *  * The warp's batch of R rows is flattened into R*V 16-byte vectors and walked with all 32
- *    lanes, UNROLL vectors per lane in flight before the first store: bytes-in-flight per SM is
- *    what hides HBM (~0.8 us) and NVSwitch (~2-3 us) latency, there is no idle lane for
- *    non-power-of-two rows and no shared-memory round trip.
+ *  * The warp's batch of R rows (~4 KiB) is flattened into R*V vectors of the widest unit the alignment
+ *    allows (32 bytes = one 256-bit access, else 16 ... 1) and walked with all 32 lanes, UNROLL vectors
+ *    per lane in flight before the first store: bytes-in-flight per SM is what hides HBM (~0.8 us)
+ *    and NVSwitch (~2-3 us) latency, there is no idle lane for non-power-of-two rows and no
+ *    shared-memory round trip.
  *  * Streaming cache policy: table reads bypass L1 allocation, dense writes are evict-first.
  *
  * Element conversion (table dtype != dense dtype) follows the reference's type_caster chain
@@ -64,7 +65,8 @@ __device__ __forceinline__ char* resolve_table_byte(const table_ref& t, uint64_t
 /* ---- vector moves with streaming cache hints ---- */
 template <int BYTES>
 struct vec_t;
-/* 32-byte unit: sm_100 has 256-bit global loads/stores (SASS LDG.E.256 / STG.E.256).  Experiment knob WG_VEC32=1. */
+/* 32-byte unit: sm_100 has 256-bit global loads/stores (SASS LDG.E.256 / STG.E.256); the default unit wherever every address,
+ * stride and the row size are multiples of 32 bytes (+2-4 % over 16-byte units, profiles/README.md round 2). */
 struct alignas(32) u32x8 {
   uint32_t v[8];
 };

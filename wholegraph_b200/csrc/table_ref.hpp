@@ -30,7 +30,7 @@ struct row_geom {
    * (an integer divide per vector runs on the XU pipe and was measured to saturate it at 96 %) */
   uint64_t div_magic;
   int units_per_row; /* vectors (copy kernels) or ALIGN-packs (converting kernels) per row */
-  int policy;        /* developer knob (WG_CACHE_POLICY): load variant | store variant << 4; 0 = default */
+  int policy;        /* load variant | store variant << 4; 0 = streaming loads (local rows), 2 = L1-allocating loads (rows that can be remote) */
 };
 
 }  // namespace wm
