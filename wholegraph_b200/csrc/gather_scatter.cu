@@ -48,11 +48,13 @@ int env_int(const char* name, int dflt)
   return dflt;
 #endif
 }
+#ifdef WG_DEV_KNOBS
 int tuned_unroll()
 {
   static const int u = env_int("WG_UNROLL", kUnroll);
   return u;
 }
+#endif
 
 int tuned_threads()
 {
