@@ -70,6 +70,27 @@ def _worker(rank, world_size, port, results):
             except RuntimeError:
                 ok = True
             assert ok
+            # same arguments everywhere, but no rank CAN allocate (no GPU): every rank gets the error -- and stays in step:
+            # the failure travels through the collectives of the allocation (fail_together) instead of skipping them
+            for mt, ml in ((wmb.MtChunked, wmb.MlDevice), (wmb.MtContinuous, wmb.MlHost), (wmb.MtDistributed, wmb.MlHost)):
+                try:
+                    wmb.malloc(1 << 20, comm.wmb_comm, mt, ml, 64)
+                    ok = False
+                except (RuntimeError, NotImplementedError) as e:  # CUDA error, or NOT_SUPPORTED (code 9 -> "not recognized")
+                    ok = "CUDA" in str(e) or "not recognized" in str(e)
+                assert ok, (mt, ml)
+                comm.barrier()  # still in step after the failed collective
+            # different custom partitions with the same total: LOGIC_ERROR on every rank (a hash of the array is compared)
+            part = [8] * world_size
+            if rank == 1:
+                part[0], part[-1] = 7, 9
+            try:
+                wmb.malloc(8 * world_size * 64, comm.wmb_comm, wmb.MtDistributed, wmb.MlDevice, 64, part)
+                ok = False
+            except RuntimeError as e:
+                ok = "ogic" in str(e)
+            assert ok
+            comm.barrier()
         results[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback
