@@ -30,3 +30,52 @@ def test_magic_division_random_interior_points():
     w = (rng.random(2_000_000) * (d.astype(np.float64) * 32 + 256)).astype(np.uint64)
     magic = ((np.uint64(1) << np.uint64(40)) + d - np.uint64(1)) // d
     assert np.array_equal((w * magic) >> np.uint64(40), w // d)
+
+
+def test_rotated_owner_walk_of_the_gradient_push_is_a_permutation():
+    """peer_push.cu: warp j of the push grid handles grouped position (j + bucket_start[(me + 1) % ws]) mod n_send.  For any
+    bucket sizes (empty buckets included) that is a bijection on [0, n_send), it starts at owner me + 1's bucket (or the
+    next non-empty one) and ends with the rank's own bucket."""
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        ws = int(rng.integers(1, 17))
+        me = int(rng.integers(0, ws))
+        counts = rng.integers(0, 50, size=ws) * (rng.random(ws) > 0.3)
+        start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        n = int(start[-1])
+        if n == 0:
+            continue
+        first = int(start[(me + 1) % ws])
+        j = np.arange(n, dtype=np.int64)
+        pos = j + first
+        pos = np.where(pos >= n, pos - n, pos)
+        assert sorted(pos.tolist()) == list(range(n))
+        owner = np.searchsorted(start, pos, side="right") - 1
+        order = [int(o) for i, o in enumerate(owner) if i == 0 or owner[i] != owner[i - 1]]
+        expect = [r % ws for r in range(me + 1, me + 1 + ws) if counts[r % ws] > 0]
+        assert order == expect, (order, expect)
+
+
+def test_long_run_dispatch_lists_every_hot_row_exactly_once():
+    """sparse_optimizer.cu: the head of a run (sorted position b with sorted[b-1] != sorted[b]) hands its row to
+    long_run_update_kernel iff b + 64 < n and sorted[b + 64] == sorted[b], i.e. iff the run is longer than 64; the run's
+    end is then the upper bound found by the binary search that starts at b + 64.  Checked against run lengths from numpy."""
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        lens = rng.choice([1, 2, 63, 64, 65, 66, 127, 128, 129, 700], size=int(rng.integers(1, 30)))
+        ids = np.sort(rng.choice(10**6, size=lens.size, replace=False))
+        s = np.repeat(ids, lens)
+        n = s.size
+        heads = [b for b in range(n) if b == 0 or s[b - 1] != s[b]]
+        listed = [b for b in heads if b + 64 < n and s[b + 64] == s[b]]
+        truth = [int(h) for h, L in zip(np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) if L > 64]
+        assert listed == truth
+        for b in listed:
+            lo, hi = b + 64, n
+            while hi - lo > 1:
+                mid = lo + (hi - lo) // 2
+                if s[mid] == s[b]:
+                    lo = mid
+                else:
+                    hi = mid
+            assert hi - b == lens[heads.index(b)]
